@@ -1,0 +1,190 @@
+"""ctypes loader for the C golden model (oracle/libvitoracle.so) and, when built, the reference's own
+CUDA decoder (oracle/_ref/libvitref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+HARD, SOFT4, SOFT8, SOFT16, FP32 = 0, 1, 2, 3, 4
+M_B32, M_B16, M_FP16 = 0x00, 0x10, 0x20
+O_B32, O_B16 = 0x000, 0x100
+REG, DPX = 0x0000, 0x1000
+FLAG_REF_OVERRUN = 1
+SEGMENTS = 6400
+EXTRA_L = 26
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libvitoracle.so")
+    src = os.path.join(_HERE, "vit_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libvitoracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        sz = C.c_size_t
+        for name in ("vo_input_size", "vo_message_len", "vo_output_size"):
+            f = getattr(L, name)
+            f.restype, f.argtypes = sz, [C.c_int, sz]
+        L.vo_options_valid_ref.restype, L.vo_options_valid_ref.argtypes = C.c_int, [C.c_int]
+        L.vo_decode.restype = C.c_int
+        L.vo_decode.argtypes = [C.c_int, C.c_void_p, C.c_void_p, sz, C.c_int, C.c_int]
+        L.vo_decode_segments.restype = C.c_int
+        L.vo_decode_segments.argtypes = [C.c_int, C.c_void_p, C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
+        L.vo_overrun_words.restype = sz
+        L.vo_overrun_words.argtypes = [C.c_int, sz, C.c_void_p, sz]
+        L.vo_encode.restype, L.vo_encode.argtypes = None, [C.c_void_p, sz, C.c_void_p]
+        L.vo_pack.restype, L.vo_pack.argtypes = None, [C.c_int, C.c_void_p, sz, C.c_float, C.c_void_p]
+        L.vo_prbs31.restype, L.vo_prbs31.argtypes = None, [C.c_uint32, C.c_void_p, sz]
+        L.vo_count_errors.restype = C.c_uint64
+        L.vo_count_errors.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p]
+        L.vo_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def input_size(options, n):
+    return lib().vo_input_size(options, n)
+
+
+def message_len(options, n):
+    return lib().vo_message_len(options, n)
+
+
+def output_size(options, n):
+    return lib().vo_output_size(options, n)
+
+
+def out_dtype(options):
+    return np.uint16 if (options & 0xF00) == O_B16 else np.uint32
+
+
+def decode(options, packed, input_num, nthreads=0, flags=0, segs=None):
+    """packed: contiguous numpy array holding vo_input_size(options, input_num) bytes."""
+    packed = np.ascontiguousarray(packed)
+    assert packed.nbytes >= input_size(options, input_num), (packed.nbytes, input_size(options, input_num))
+    out = np.zeros(output_size(options, input_num) // np.dtype(out_dtype(options)).itemsize, out_dtype(options))
+    if segs is None:
+        rc = lib().vo_decode(options, _ptr(packed), _ptr(out), input_num, nthreads, flags)
+    else:
+        rc = lib().vo_decode_segments(options, _ptr(packed), _ptr(out), input_num, segs[0], segs[1], nthreads, flags)
+    if rc != 0:
+        raise ValueError("oracle does not define option combination 0x%x" % options)
+    return out
+
+
+def overrun_words(options, input_num):
+    n = lib().vo_overrun_words(options, input_num, None, 0)
+    idx = np.zeros(max(n, 1), np.uint64)
+    lib().vo_overrun_words(options, input_num, _ptr(idx), n)
+    return idx[:n]
+
+
+def encode(bits):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    coded = np.empty(2 * bits.size, np.uint8)
+    lib().vo_encode(_ptr(bits), bits.size, _ptr(coded))
+    return coded
+
+
+def pack(input_type, soft, scale=1.0):
+    """soft: float32 array of channel values (+-1 based).  Returns the packed encPack_t stream."""
+    soft = np.ascontiguousarray(soft, np.float32)
+    n = soft.size
+    if input_type == FP32:
+        out = np.empty(n, np.float32)
+    else:
+        per = {HARD: 32, SOFT4: 8, SOFT8: 4, SOFT16: 2}[input_type]
+        assert n % per == 0, "symbol count must fill whole int32 packs"
+        out = np.empty(n // per, np.int32)
+    lib().vo_pack(input_type, _ptr(soft), n, scale, _ptr(out))
+    return out
+
+
+def prbs31(seed, n):
+    bits = np.empty(n, np.uint8)
+    lib().vo_prbs31(seed, _ptr(bits), n)
+    return bits
+
+
+def count_errors(options, out, message_len_, bits):
+    out = np.ascontiguousarray(out)
+    bits = np.ascontiguousarray(bits, np.uint8)
+    return int(lib().vo_count_errors(options, _ptr(out), message_len_, _ptr(bits)))
+
+
+def num_threads():
+    return lib().vo_num_threads()
+
+
+def make_channel(n_bits, input_type, snr_db=None, seed=1, scale=40000.0, prbs=False, sigma=None):
+    """Seeded twin of the reference harness's source -> encoder -> AWGN -> packer chain
+    (main.cpp:131-138): sigma = 10^(-snr/5), scale 40000.  Returns (bits, packed, input_num)."""
+    rng = np.random.default_rng(seed)
+    bits = prbs31(0x7FFFFFFF ^ seed, n_bits) if prbs else rng.integers(0, 2, n_bits, dtype=np.uint8)
+    coded = encode(bits)
+    soft = coded.astype(np.float32) * 2.0 - 1.0
+    if sigma is None and snr_db is not None:
+        sigma = 10.0 ** (-snr_db / 5.0)
+    if sigma:
+        soft = soft + rng.standard_normal(soft.size, dtype=np.float32) * np.float32(sigma)
+    return bits, pack(input_type, soft, scale), 2 * n_bits
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own CUDA decoder (needs a GPU to run; size helpers work anywhere)
+
+_ref = None
+
+
+def ref_lib():
+    """oracle/_ref/libvitref.so or None."""
+    global _ref
+    if _ref is None:
+        so = os.path.join(_HERE, "_ref", "libvitref.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_run.restype = C.c_int
+        L.ref_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_float)]
+        L.ref_sizes.restype = C.c_int
+        L.ref_sizes.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ref_device_count.restype = C.c_int
+        _ref = L
+    return _ref
+
+
+def ref_sizes(options, n):
+    v = (C.c_size_t * 3)()
+    rc = ref_lib().ref_sizes(options, n, v)
+    return None if rc else (v[0], v[1], v[2])
+
+
+def ref_decode(options, packed, input_num):
+    """Run the unmodified reference decoder (GPU).  Returns (out, kernel_ms)."""
+    packed = np.ascontiguousarray(packed)
+    nwords = output_size(options, input_num) // np.dtype(out_dtype(options)).itemsize
+    out = np.zeros(nwords + 8, out_dtype(options))  # slack: the reference's O_B16 over-run stores are device-side only
+    ms = C.c_float(0)
+    rc = ref_lib().ref_run(options, _ptr(packed), _ptr(out), input_num, C.byref(ms))
+    if rc != 0:
+        raise ValueError("reference rejects option combination 0x%x" % options)
+    return out[:nwords], ms.value
