@@ -1,0 +1,149 @@
+"""B200-native Viterbi decoder: Python mirror of the reference's host class.
+
+`ViterbiCUDA(options)` mirrors `template<int options> class ViterbiCUDA`
+(reference src/viterbi/viterbi.h:91-152): same method names, same argument meaning (every size is
+a count of CODED SYMBOLS), same option bitfield.  Every call goes through the C ABI in
+include/vit_b200.h (libvitb200.so, hand-written sm_100a kernels).  There is no CPU path: if the
+shared library is missing or CUDA fails, these functions raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+
+# option bitfield, reference src/viterbi/viterbi.h:7-20
+HARD, SOFT4, SOFT8, SOFT16, FP32 = 0x0, 0x1, 0x2, 0x3, 0x4
+M_B32, M_B16, M_FP16 = 0x00, 0x10, 0x20
+O_B32, O_B16 = 0x000, 0x100
+REG, DPX = 0x0000, 0x1000
+CHANNEL_MASK, METRIC_MASK, DECODE_MASK, COMP_MASK = 0xF, 0xF0, 0xF00, 0xF000
+
+# window constants, reference viterbi.h:61-79
+constLen, polyn1, polyn2 = 7, 0o171, 0o133
+extraL, extraR, slideSize, forwardLen = 26, 38, 32, 96
+SEGMENTS = 6400
+
+
+class ViterbiError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The C-ABI library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ViterbiError("libvitb200.so is not built: run `make -C %s/csrc` (or __graft_entry__.build())" % _HERE)
+        L = C.CDLL(LIB_PATH)
+        sz, vp = C.c_size_t, C.c_void_p
+        L.vit_create.restype, L.vit_create.argtypes = C.c_int, [C.POINTER(vp), C.c_int, C.c_int, sz]
+        L.vit_destroy.restype, L.vit_destroy.argtypes = None, [vp]
+        L.vit_run.restype, L.vit_run.argtypes = C.c_int, [vp, vp, vp, sz, C.POINTER(C.c_float)]
+        L.vit_run_device.restype = C.c_int
+        L.vit_run_device.argtypes = [vp, vp, vp, sz, vp, C.POINTER(C.c_float)]
+        L.vit_run_device_batch.restype = C.c_int
+        L.vit_run_device_batch.argtypes = [vp, vp, vp, sz, sz, sz, sz, vp, C.POINTER(C.c_float)]
+        for n in ("vit_input_size", "vit_message_len", "vit_output_size"):
+            f = getattr(L, n)
+            f.restype, f.argtypes = sz, [C.c_int, sz]
+        L.vit_options_valid.restype, L.vit_options_valid.argtypes = C.c_int, [C.c_int]
+        L.vit_options_valid_ref.restype, L.vit_options_valid_ref.argtypes = C.c_int, [C.c_int]
+        L.vit_kernel_info.restype = C.c_int
+        L.vit_kernel_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4
+        L.vit_launch_count.restype, L.vit_launch_count.argtypes = C.c_ulonglong, [vp]
+        L.vit_set_segments.restype, L.vit_set_segments.argtypes = C.c_int, [vp, C.c_uint]
+        L.vit_last_error.restype, L.vit_last_error.argtypes = C.c_char_p, []
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise ViterbiError("vit error %d: %s" % (rc, lib().vit_last_error().decode()))
+
+
+def options_valid(options):
+    return bool(lib().vit_options_valid(options))
+
+
+def options_valid_ref(options):
+    return bool(lib().vit_options_valid_ref(options))
+
+
+def parse_options(input="h", metric="b32", output="b32", comp="reg"):
+    """The ./main flag values (reference src/main.cpp:211-254) -> option bitfield."""
+    i = {"HARD": HARD, "h": HARD, "SOFT4": SOFT4, "s4": SOFT4, "SOFT8": SOFT8, "s8": SOFT8,
+         "SOFT16": SOFT16, "s16": SOFT16, "FP32": FP32, "f": FP32}[input]
+    m = {"b16": M_B16, "b32": M_B32, "f16": M_FP16}[metric]
+    o = {"b16": O_B16, "b32": O_B32}[output]
+    c = {"REG": REG, "reg": REG, "DPX": DPX, "dpx": DPX}[comp]
+    return i | m | o | c
+
+
+class ViterbiCUDA:
+    """Mirror of reference `ViterbiCUDA<options>` (viterbi.h:91-152)."""
+
+    def __init__(self, options=0, inputNum=0, device=0):
+        self.options = int(options)
+        self._h = C.c_void_p()
+        _check(lib().vit_create(C.byref(self._h), self.options, int(device), int(inputNum)))
+        self.device = int(device)
+        self.bitsPerPack = 16 if (self.options & DECODE_MASK) == O_B16 else 32
+        self.decPack_t = np.uint16 if self.bitsPerPack == 16 else np.uint32
+        self.encPack_t = np.float32 if (self.options & CHANNEL_MASK) == FP32 else np.int32
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().vit_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # reference viterbi.cu:63-92
+    def getInputSize(self, inputNum):
+        return lib().vit_input_size(self.options, inputNum)
+
+    def getMessageLen(self, inputNum):
+        return lib().vit_message_len(self.options, inputNum)
+
+    def getOutputSize(self, inputNum):
+        return lib().vit_output_size(self.options, inputNum)
+
+    def run(self, input_h, inputNum, output_h=None, want_kernel_time=False):
+        """reference ViterbiCUDA::run (viterbi.cu:210-238): host numpy buffers in and out.
+        Returns output_h, or (output_h, kernel_ms) when want_kernel_time."""
+        input_h = np.ascontiguousarray(input_h)
+        if input_h.nbytes < self.getInputSize(inputNum):
+            raise ViterbiError("input buffer holds %d bytes, %d needed" % (input_h.nbytes, self.getInputSize(inputNum)))
+        nwords = self.getOutputSize(inputNum) // np.dtype(self.decPack_t).itemsize
+        if output_h is None:
+            output_h = np.empty(nwords, self.decPack_t)
+        ms = C.c_float(0)
+        _check(lib().vit_run(self._h, input_h.ctypes.data, output_h.ctypes.data, inputNum,
+                             C.byref(ms) if want_kernel_time else None))
+        return (output_h, ms.value) if want_kernel_time else output_h
+
+    def run_device(self, in_ptr, out_ptr, inputNum, stream=0, want_kernel_time=False,
+                   nstreams=1, in_stride=0, out_stride=0):
+        """Device-resident decode: raw device pointers (e.g. torch tensor .data_ptr())."""
+        ms = C.c_float(0)
+        _check(lib().vit_run_device_batch(self._h, in_ptr, out_ptr, inputNum, nstreams, in_stride, out_stride,
+                                          stream, C.byref(ms) if want_kernel_time else None))
+        return ms.value if want_kernel_time else None
+
+    def kernel_info(self):
+        v = [C.c_int(0) for _ in range(4)]
+        _check(lib().vit_kernel_info(self.options, *[C.byref(x) for x in v]))
+        return {"regs": v[0].value, "smem_bytes": v[1].value, "block_threads": v[2].value, "segs_per_block": v[3].value}
+
+    def launch_count(self):
+        return int(lib().vit_launch_count(self._h))
+
+    def set_segments(self, segments):
+        _check(lib().vit_set_segments(self._h, segments))

@@ -1,0 +1,748 @@
+// vit_kernel.cuh -- fused, persistent-per-segment Viterbi decode kernel for sm_100a (B200).
+//
+// Replaces the reference's viterbi_core kernel and its three device headers
+// (reference src/viterbi/viterbi.cu:144-207, viterbiBM.cuh, viterbiACS.cuh, viterbiTB.cuh) with a
+// different mapping of the same algorithm (K=7, 64 states, polys 0171/0133, 6400 stream segments,
+// 64-stage warm-up, register-exchange survivor words, 96-stage ring, traceback from state 0):
+//
+//   * 8 lanes per stream segment, 4 segments per warp (the reference: 32 lanes per segment).
+//     Each lane owns 8 trellis states: 4 packed int16x2 / half2 registers, or 8 int32 registers.
+//   * In-place "rotating" state map: position q (6 bits) holds state rotr6(q, phase) after a stage
+//     with phase = stage % 6.  q bits 0,2,4 are lane bits, q bits 1,3,5 are register/half bits, so
+//     only phases 1,3,5 need warp shuffles; phases 2,4 are register-local and phase 0 is a
+//     half-swap (packed cores) or register-local (int32 core).
+//   * Everything is unrolled over the 96-stage period lcm(6 phases, 32-stage slide): all index
+//     math, shuffle masks, branch-metric operand choices and survivor-bit positions are immediates.
+//   * Branch metrics: the channel words arrive by 16-byte cp.async into a double-buffered raw
+//     staging area, are unpacked once per 48 stages into a shared-memory table of ready-to-add
+//     packed operands (one 8-byte entry per stage x lane-class), and each ACS stage costs one
+//     LDS.64 per lane.
+//   * Survivors: 32-bit register-exchange words moved with predicated selects (VIMNMX.S16x2 yields
+//     both decision predicates).  The decision bits themselves are never shifted in one by one:
+//     the last 6 message bits of a survivor are its state index, so they are OR-ed in as a 6-bit
+//     immediate field every 6 stages.
+//   * The one-pointer ring (3 x 64 words per segment) lives in shared memory, not global.
+//
+// The same source compiles for the host (VIT_HOST_EMU) where 32 fibers run the warp in lockstep;
+// tests/emu uses that to check the kernel logic against the oracle without a GPU.  The host build
+// is test scaffolding only and is never linked into the product library.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#define VIT_HD __host__ __device__ __forceinline__
+#define VIT_D __device__ __forceinline__
+#else
+#define VIT_HD inline
+#define VIT_D inline
+#endif
+
+namespace vitk {
+
+enum { IN_HARD = 0, IN_S4 = 1, IN_S8 = 2, IN_S16 = 3, IN_F32 = 4 };
+enum { MET_B32 = 0, MET_B16 = 1, MET_F16 = 2 };
+
+struct KParams {
+    const uint8_t* in;              // stream 0 channel words
+    uint8_t* out;                   // stream 0 decoded packs
+    unsigned long long in_stride;   // bytes between consecutive streams
+    unsigned long long out_stride;
+    unsigned long long in_bytes;    // valid channel bytes per stream (reads beyond are zero-filled)
+    unsigned long long packs;       // decoded packs per stream (messageLen / bitsPerPack)
+    unsigned segments;              // stream segments (reference: 6400, viterbi.cu:19)
+    unsigned nstreams;
+};
+
+// ------------------------------------------------------------------------------------------------
+// compile-time trellis geometry
+// ------------------------------------------------------------------------------------------------
+constexpr int mod6(int x) { return ((x % 6) + 6) % 6; }
+constexpr int LANES_PER_SEG = 8;
+constexpr int SEGS_PER_WARP = 4;
+constexpr int CHUNK = 48;       // stages per branch-metric table build
+constexpr int SUPER = 96;       // unroll period
+
+// symbol bit 0 (poly 0171) depends on q bits {p+4,p+3,p+2}, symbol bit 1 (poly 0133) on {p+3,p+2,p}
+// (indices mod 6); the butterfly bit (p+5) cancels because both polynomials tap bits 0 and 6.
+constexpr bool inset0(int p, int qb) { return qb == mod6(p + 4) || qb == mod6(p + 3) || qb == mod6(p + 2); }
+constexpr bool inset1(int p, int qb) { return qb == mod6(p + 3) || qb == mod6(p + 2) || qb == mod6(p); }
+
+// lane bit k <-> q bit 2k ; register/half bit k <-> q bit 2k+1
+constexpr int lane_mask(int which, int p) {
+    int m = 0;
+    for (int k = 0; k < 3; k++) m |= ((which ? inset1(p, 2 * k) : inset0(p, 2 * k)) ? 1 : 0) << k;
+    return m;
+}
+constexpr int reg_mask(int which, int p) {
+    int m = 0;
+    for (int k = 0; k < 3; k++) m |= ((which ? inset1(p, 2 * k + 1) : inset0(p, 2 * k + 1)) ? 1 : 0) << k;
+    return m;
+}
+constexpr int par3(int v) { return ((v >> 0) ^ (v >> 1) ^ (v >> 2)) & 1; }
+
+// operand type of the own-branch metric for register index s8 at phase p:
+//   0: +X   1: +Y   2: -Y   3: -X      (X = D0+D1, Y = D0-D1 of the lane-class adjusted symbols)
+constexpr int bm_type(int s8, int p) {
+    int st0 = par3(s8 & reg_mask(0, p)), st1 = par3(s8 & reg_mask(1, p));
+    return st0 == 0 ? (st1 == 0 ? 0 : 1) : (st1 == 0 ? 2 : 3);
+}
+// how the high half of a packed operand differs from the low half (does q5 tap poly0 / poly1)
+constexpr int half_variant(int p) { return (inset0(p, 5) ? 2 : 0) | (inset1(p, 5) ? 1 : 0); }
+
+// stage kinds
+enum { KIND_HALF = 0, KIND_LANE = 1, KIND_REG = 2 };
+constexpr int beta(int p) { return mod6(p + 5); }  // butterfly q bit
+template <int MET>
+constexpr int stage_kind(int p) {
+    return (beta(p) % 2 == 0) ? KIND_LANE : ((beta(p) == 5 && MET != MET_B32) ? KIND_HALF : KIND_REG);
+}
+constexpr int stage_bit(int p) { return beta(p) / 2; }  // lane bit or register bit index
+
+// 6-bit survivor field (oldest message bit in the MSB) contributed by position bits at phase p
+constexpr int field_of_qbit(int qb, int p) { return 1 << (5 - mod6(qb - p)); }
+constexpr int static_field(int s8, int p) {
+    int f = 0;
+    for (int k = 0; k < 3; k++) if ((s8 >> k) & 1) f |= field_of_qbit(2 * k + 1, p);
+    return f;
+}
+
+template <int IN> struct InTraits;
+template <> struct InTraits<IN_HARD> { static constexpr int B96 = 24; };
+template <> struct InTraits<IN_S4> { static constexpr int B96 = 96; };
+template <> struct InTraits<IN_S8> { static constexpr int B96 = 192; };
+template <> struct InTraits<IN_S16> { static constexpr int B96 = 384; };
+template <> struct InTraits<IN_F32> { static constexpr int B96 = 768; };
+template <int IN> constexpr int raw_pieces() { return (InTraits<IN>::B96 + 12 + 15) / 16; }
+
+// offset added to int16 branch metrics so every packed operand is a non-negative 16-bit value
+// (lets plain 32-bit adds act as two independent 16-bit adds); == max |symbol sum| / 1
+template <int IN> constexpr int b16_offset() { return IN == IN_HARD ? 1 : IN == IN_S8 ? 256 : 16; }
+
+// shared memory carve-up (per warp; one warp per block)
+template <int IN> struct Smem {
+    static constexpr int BM_BYTES = CHUNK * SEGS_PER_WARP * 4 * 8;                 // 6144
+    static constexpr int RAW_SEG = raw_pieces<IN>() * 16;
+    static constexpr int RAW_BYTES = 2 * SEGS_PER_WARP * RAW_SEG;
+    static constexpr int RING_BYTES = 3 * SEGS_PER_WARP * 64 * 4;                  // 3072
+    static constexpr int LUT_BYTES = 3 * 64;
+    static constexpr int OFF_BM = 0;
+    static constexpr int OFF_RAW = OFF_BM + BM_BYTES;
+    static constexpr int OFF_RING = OFF_RAW + RAW_BYTES;
+    static constexpr int OFF_LUT = OFF_RING + RING_BYTES;
+    static constexpr int TOTAL = OFF_LUT + LUT_BYTES;
+};
+
+// ------------------------------------------------------------------------------------------------
+// SIMT primitives: device intrinsics, or the host emulator's lockstep fibers
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+VIT_D uint32_t shfl_xor(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+VIT_D uint32_t shfl_idx(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+VIT_D void syncwarp() { __syncwarp(); }
+VIT_D void cp_async16(void* smem_dst, const void* gsrc, unsigned src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+VIT_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> VIT_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+VIT_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+VIT_D uint32_t brev32(uint32_t v) { return __brev(v); }
+#else
+uint32_t emu_shfl_xor(uint32_t v, int m);
+uint32_t emu_shfl_idx(uint32_t v, int src);
+void emu_syncwarp();
+inline uint32_t shfl_xor(uint32_t v, int m) { return emu_shfl_xor(v, m); }
+inline uint32_t shfl_idx(uint32_t v, int src) { return emu_shfl_idx(v, src); }
+inline void syncwarp() { emu_syncwarp(); }
+inline void cp_async16(void* dst, const void* src, unsigned n) {
+    uint8_t* d = (uint8_t*)dst;
+    const uint8_t* s = (const uint8_t*)src;
+    for (unsigned i = 0; i < 16; i++) d[i] = i < n ? s[i] : 0;
+}
+inline void cp_async_commit() {}
+template <int N> inline void cp_async_wait() {}
+inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+    uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t sel = (s >> (4 * i)) & 0xf;
+        uint32_t byte = (uint32_t)(v >> (8 * (sel & 7))) & 0xff;
+        if (sel & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+inline uint32_t brev32(uint32_t v) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// metric cores: candidate = metric +/- operand, max with "partner chosen" predicates
+// ------------------------------------------------------------------------------------------------
+#if !defined(__CUDA_ARCH__)
+// host model of IEEE half for small exact integers (|v| < 2048): we only ever hold integers, so a
+// float pair stands in for half2 on the host; the device uses real __half2 arithmetic.
+struct EmuH2 { float lo, hi; };
+inline uint32_t emu_h2_pack(EmuH2 v) {
+    // store as two int16 two's-complement integers (host emulation of exact-integer halves)
+    return ((uint32_t)(uint16_t)(int16_t)v.lo) | ((uint32_t)(uint16_t)(int16_t)v.hi << 16);
+}
+inline EmuH2 emu_h2_unpack(uint32_t w) { return EmuH2{(float)(int16_t)(w & 0xffff), (float)(int16_t)(w >> 16)}; }
+#endif
+
+template <int MET, int IN> struct Core;
+
+// ---- int16x2: non-negative 15-bit metrics, operands carry a +offset --------------------------
+template <int IN> struct Core<MET_B16, IN> {
+    static constexpr bool PACKED = true;
+    static constexpr uint32_t K2 = (uint32_t)(2 * b16_offset<IN>()) * 0x10001u;
+    static VIT_HD uint32_t plus(uint32_t pm, uint32_t w) { return pm + w; }
+    static VIT_HD uint32_t minus(uint32_t pm, uint32_t w) { return pm - w + K2; }
+    // returns max(partner, own); p* = partner chosen; partner wins ties (reference int16 core,
+    // viterbiACS.cuh:112-119,215-220: __vibmax_s16x2(partner - bm, own + bm) -> pred = (a >= b))
+    static VIT_HD uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool /*own_wins_tie*/) {
+#if defined(__CUDA_ARCH__)
+        return __vibmax_s16x2(part, own, &p_hi, &p_lo);
+#else
+        int16_t al = (int16_t)(part & 0xffff), ah = (int16_t)(part >> 16);
+        int16_t bl = (int16_t)(own & 0xffff), bh = (int16_t)(own >> 16);
+        p_lo = al >= bl; p_hi = ah >= bh;
+        return (uint32_t)(uint16_t)(p_lo ? al : bl) | ((uint32_t)(uint16_t)(p_hi ? ah : bh) << 16);
+#endif
+    }
+    static VIT_HD uint32_t vmin(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+        return __vmins2(a, b);
+#else
+        int16_t al = (int16_t)(a & 0xffff), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xffff), bh = (int16_t)(b >> 16);
+        return (uint32_t)(uint16_t)(al < bl ? al : bl) | ((uint32_t)(uint16_t)(ah < bh ? ah : bh) << 16);
+#endif
+    }
+    static VIT_HD uint32_t sub(uint32_t a, uint32_t m) { return a - m; }   // per-half, no borrow: a >= m
+    static VIT_HD uint32_t enc(int v) { return (uint32_t)(v + b16_offset<IN>()) & 0xffffu; }
+    static VIT_HD uint32_t zero() { return 0; }
+};
+
+// ---- half2: exact small integers on the FP16 pipe ---------------------------------------------
+template <int IN> struct Core<MET_F16, IN> {
+    static constexpr bool PACKED = true;
+#if defined(__CUDA_ARCH__)
+    static VIT_D __half2 h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
+    static VIT_D uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+    static VIT_D uint32_t plus(uint32_t pm, uint32_t w) { return u32(__hadd2(h2(pm), h2(w))); }
+    static VIT_D uint32_t minus(uint32_t pm, uint32_t w) { return u32(__hsub2(h2(pm), h2(w))); }
+    // own wins ties (reference half2 core, viterbiACS.cuh:146-157,249-256: __hlt2_mask(own, partner))
+    static VIT_D uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool) {
+        __half2 a = h2(part), b = h2(own);
+        p_lo = __hgt(__low2half(a), __low2half(b));
+        p_hi = __hgt(__high2half(a), __high2half(b));
+        return u32(__hmax2(a, b));
+    }
+    static VIT_D uint32_t vmin(uint32_t a, uint32_t b) { return u32(__hmin2(h2(a), h2(b))); }
+    static VIT_D uint32_t sub(uint32_t a, uint32_t m) { return u32(__hsub2(h2(a), h2(m))); }
+    static VIT_D uint32_t enc(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v)); }
+#else
+    static uint32_t plus(uint32_t pm, uint32_t w) { EmuH2 a = emu_h2_unpack(pm), b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{a.lo + b.lo, a.hi + b.hi}); }
+    static uint32_t minus(uint32_t pm, uint32_t w) { EmuH2 a = emu_h2_unpack(pm), b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{a.lo - b.lo, a.hi - b.hi}); }
+    static uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool) {
+        EmuH2 a = emu_h2_unpack(part), b = emu_h2_unpack(own);
+        p_lo = a.lo > b.lo; p_hi = a.hi > b.hi;
+        return emu_h2_pack(EmuH2{p_lo ? a.lo : b.lo, p_hi ? a.hi : b.hi});
+    }
+    static uint32_t vmin(uint32_t a, uint32_t b) { EmuH2 x = emu_h2_unpack(a), y = emu_h2_unpack(b); return emu_h2_pack(EmuH2{x.lo < y.lo ? x.lo : y.lo, x.hi < y.hi ? x.hi : y.hi}); }
+    static uint32_t sub(uint32_t a, uint32_t m) { return minus(a, m); }
+    static uint32_t enc(int v) { return (uint32_t)(uint16_t)(int16_t)v; }
+#endif
+    static VIT_HD uint32_t zero() { return 0; }
+};
+
+// ---- int32: one state per register --------------------------------------------------------------
+template <int IN> struct Core<MET_B32, IN> {
+    static constexpr bool PACKED = false;
+    static VIT_HD uint32_t plus(uint32_t pm, uint32_t w) { return pm + w; }
+    static VIT_HD uint32_t minus(uint32_t pm, uint32_t w) { return pm - w; }
+    // partner wins ties except where the reference's phase-0 rule makes the odd predecessor win
+    // (viterbiACS.cuh:136-142: both selfPM compares are "odd-candidate >= even-candidate")
+    static VIT_HD uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool own_wins_tie) {
+        int a = (int)part, b = (int)own;
+        bool p = own_wins_tie ? (a > b) : (a >= b);
+        p_lo = p; p_hi = p;
+        return (uint32_t)(p ? a : b);
+    }
+    static VIT_HD uint32_t vmin(uint32_t a, uint32_t b) { return (uint32_t)((int)a < (int)b ? (int)a : (int)b); }
+    static VIT_HD uint32_t sub(uint32_t a, uint32_t m) { return a - m; }
+    static VIT_HD uint32_t enc(int v) { return (uint32_t)v; }
+    static VIT_HD uint32_t zero() { return 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-lane decoder state
+// ------------------------------------------------------------------------------------------------
+template <int MET> struct LaneState {
+    static constexpr int NPM = (MET == MET_B32) ? 8 : 4;
+    uint32_t pm[NPM];
+    uint32_t pp[8];
+};
+
+// candidate of `metric` along the branch whose operand type is `type` (see bm_type), given the
+// table entry (w0 = X word, w1 = Y word); `opposite` = the other branch into the same state
+template <class C, int TYPE, bool OPPOSITE>
+VIT_HD uint32_t cand(uint32_t metric, uint32_t w0, uint32_t w1) {
+    constexpr bool useY = (TYPE == 1 || TYPE == 2);
+    constexpr bool neg = ((TYPE == 2 || TYPE == 3) != OPPOSITE);
+    return neg ? C::minus(metric, useY ? w1 : w0) : C::plus(metric, useY ? w1 : w0);
+}
+
+// one trellis stage at phase P (static).  lane bits are the low 3 bits of the lane id.
+template <int MET, int IN, int P>
+VIT_HD void acs_stage(LaneState<MET>& s, uint32_t w0, uint32_t w1) {
+    using C = Core<MET, IN>;
+    constexpr int KIND = stage_kind<MET>(P);
+    constexpr int BIT = stage_bit(P);
+    if constexpr (KIND == KIND_LANE) {
+        constexpr int XM = 1 << BIT;
+        uint32_t ppm[LaneState<MET>::NPM], ppp[8];
+#pragma unroll
+        for (int r = 0; r < LaneState<MET>::NPM; r++) ppm[r] = shfl_xor(s.pm[r], XM);
+#pragma unroll
+        for (int k = 0; k < 8; k++) ppp[k] = shfl_xor(s.pp[k], XM);
+        if constexpr (C::PACKED) {
+#define VIT_LANE_PACKED(r)                                                                        \
+    {                                                                                             \
+        bool pl, ph;                                                                              \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], w0, w1);                             \
+        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], w0, w1);                               \
+        s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
+        s.pp[r] = pl ? ppp[r] : s.pp[r];                                                          \
+        s.pp[r + 4] = ph ? ppp[r + 4] : s.pp[r + 4];                                              \
+    }
+            VIT_LANE_PACKED(0) VIT_LANE_PACKED(1) VIT_LANE_PACKED(2) VIT_LANE_PACKED(3)
+#undef VIT_LANE_PACKED
+        } else {
+#define VIT_LANE_B32(r)                                                                           \
+    {                                                                                             \
+        bool pl, ph;                                                                              \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], w0, w1);                             \
+        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], w0, w1);                               \
+        s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
+        s.pp[r] = pl ? ppp[r] : s.pp[r];                                                          \
+    }
+            VIT_LANE_B32(0) VIT_LANE_B32(1) VIT_LANE_B32(2) VIT_LANE_B32(3)
+            VIT_LANE_B32(4) VIT_LANE_B32(5) VIT_LANE_B32(6) VIT_LANE_B32(7)
+#undef VIT_LANE_B32
+        }
+    } else if constexpr (KIND == KIND_HALF) {
+        // packed cores, phase 0: the two predecessors are the two halves of the same register
+#define VIT_HALF(r)                                                                               \
+    {                                                                                             \
+        bool pl, ph;                                                                              \
+        uint32_t sw = prmt(s.pm[r], 0, 0x1032);                                                   \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], w0, w1);                             \
+        uint32_t pc = cand<C, bm_type(r, P), true>(sw, w0, w1);                                   \
+        s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
+        uint32_t a = s.pp[r], b = s.pp[r + 4];                                                    \
+        s.pp[r] = pl ? b : a;                                                                     \
+        s.pp[r + 4] = ph ? a : b;                                                                 \
+    }
+        VIT_HALF(0) VIT_HALF(1) VIT_HALF(2) VIT_HALF(3)
+#undef VIT_HALF
+    } else {
+        // register-local butterfly on register-index bit BIT
+        if constexpr (C::PACKED) {
+#define VIT_REG_PACKED(ra)                                                                        \
+    if constexpr (((ra >> BIT) & 1) == 0) {                                                       \
+        constexpr int rb = ra | (1 << BIT);                                                       \
+        bool al, ah, bl, bh;                                                                      \
+        uint32_t ea = s.pm[ra], eb = s.pm[rb];                                                    \
+        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, w0, w1),                        \
+                                cand<C, bm_type(ra, P), false>(ea, w0, w1), al, ah, false);       \
+        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, w0, w1),                        \
+                                cand<C, bm_type(rb, P), false>(eb, w0, w1), bl, bh, false);       \
+        s.pm[ra] = na; s.pm[rb] = nb;                                                             \
+        uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb], pa1 = s.pp[ra + 4], pb1 = s.pp[rb + 4];          \
+        s.pp[ra] = al ? pb0 : pa0; s.pp[rb] = bl ? pa0 : pb0;                                     \
+        s.pp[ra + 4] = ah ? pb1 : pa1; s.pp[rb + 4] = bh ? pa1 : pb1;                             \
+    }
+            VIT_REG_PACKED(0) VIT_REG_PACKED(1) VIT_REG_PACKED(2) VIT_REG_PACKED(3)
+#undef VIT_REG_PACKED
+        } else {
+            // reference int32 core, phase 0: the odd predecessor wins ties for both new states
+            // (viterbiACS.cuh:136-142); all other phases: partner wins ties (viterbiACS.cuh:238-245)
+            constexpr bool ODD_WINS = (P == 0);
+#define VIT_REG_B32(ra)                                                                           \
+    if constexpr (((ra >> BIT) & 1) == 0) {                                                       \
+        constexpr int rb = ra | (1 << BIT);                                                       \
+        bool al, ah, bl, bh;                                                                      \
+        uint32_t ea = s.pm[ra], eb = s.pm[rb];                                                    \
+        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, w0, w1),                        \
+                                cand<C, bm_type(ra, P), false>(ea, w0, w1), al, ah, false);       \
+        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, w0, w1),                        \
+                                cand<C, bm_type(rb, P), false>(eb, w0, w1), bl, bh, ODD_WINS);    \
+        s.pm[ra] = na; s.pm[rb] = nb;                                                             \
+        uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb];                                                  \
+        s.pp[ra] = al ? pb0 : pa0; s.pp[rb] = bl ? pa0 : pb0;                                     \
+    }
+            VIT_REG_B32(0) VIT_REG_B32(1) VIT_REG_B32(2) VIT_REG_B32(3)
+            VIT_REG_B32(4) VIT_REG_B32(5) VIT_REG_B32(6) VIT_REG_B32(7)
+#undef VIT_REG_B32
+        }
+    }
+}
+
+// OR the survivors' newest message bits (== state index bits) into the register-exchange words.
+// NB bits (6 or 2) taken from the top of the 6-bit field, placed at bit SHIFT.
+template <int MET, int P, int SHIFT, int NB, bool ASSIGN>
+VIT_HD void insert_field(LaneState<MET>& s, uint32_t lane_field) {
+    const uint32_t lf = (NB == 6 ? lane_field : (lane_field >> 4)) << SHIFT;
+#define VIT_INS(k)                                                                                \
+    {                                                                                             \
+        constexpr uint32_t sf = (uint32_t)(NB == 6 ? static_field(k, P) : (static_field(k, P) >> 4)) << SHIFT; \
+        s.pp[k] = ASSIGN ? (lf | sf) : (s.pp[k] | lf | sf);                                       \
+    }
+    VIT_INS(0) VIT_INS(1) VIT_INS(2) VIT_INS(3) VIT_INS(4) VIT_INS(5) VIT_INS(6) VIT_INS(7)
+#undef VIT_INS
+}
+
+// position index (lane*8 + reg) of state `st` at phase p
+constexpr int pos_index_of_state(int st, int p) {
+    int q = ((st << p) | (st >> (6 - p))) & 63;  // rotl6
+    int l = ((q >> 0) & 1) | (((q >> 2) & 1) << 1) | (((q >> 4) & 1) << 2);
+    int r = ((q >> 1) & 1) | (((q >> 3) & 1) << 1) | (((q >> 5) & 1) << 2);
+    return l * 8 + r;
+}
+
+VIT_HD uint32_t lane_field_of(int l, int p) {
+    uint32_t f = 0;
+    for (int k = 0; k < 3; k++)
+        if ((l >> k) & 1) f |= 1u << (5 - mod6(2 * k - p));
+    return f;
+}
+VIT_HD int lane_class_of(int l, int p) {
+    int c0 = 0, c1 = 0;
+    for (int k = 0; k < 3; k++) {
+        if (((l >> k) & 1) && inset0(p, 2 * k)) c0 ^= 1;
+        if (((l >> k) & 1) && inset1(p, 2 * k)) c1 ^= 1;
+    }
+    return c0 * 2 + c1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// branch-metric table build: lane j of the group unpacks stage base+P+6j (P static) and writes the
+// four lane-class entries {W0,W1} for it.
+// ------------------------------------------------------------------------------------------------
+template <int MET, int IN>
+VIT_HD void load_symbols(const uint8_t* raw, int rel_stage, int& d0, int& d1, float& f0, float& f1) {
+    // raw points at the byte holding the first stage of this superchunk (word aligned)
+    d0 = d1 = 0; f0 = f1 = 0.f;
+    if constexpr (IN == IN_HARD) {
+        // 32 symbols per int32, MSB first (reference viterbiBM.cuh:33-40)
+        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 4));
+        uint32_t rx = (w >> (30 - 2 * (rel_stage & 15))) & 3u;
+        d0 = 2 * (int)(rx >> 1) - 1; d1 = 2 * (int)(rx & 1) - 1;   // +-1, halved after the sum
+    } else if constexpr (IN == IN_S4) {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 2));   // viterbiBM.cuh:64-75
+        int sh = 24 - 8 * (rel_stage & 3);
+        d0 = ((int)(w << (24 - sh))) >> 28;
+        d1 = ((int)(w << (28 - sh))) >> 28;
+    } else if constexpr (IN == IN_S8) {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 1));   // viterbiBM.cuh:97-100
+        int sh = 16 - 16 * (rel_stage & 1);
+        d0 = (int)(int8_t)(w >> (sh + 8));
+        d1 = (int)(int8_t)(w >> sh);
+        if constexpr (MET == MET_F16) { d0 >>= 3; d1 >>= 3; }       // extension: keep half2 exact
+    } else if constexpr (IN == IN_S16) {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * rel_stage);          // viterbiBM.cuh:121-124
+        d0 = (int)(int16_t)(w >> 16);
+        d1 = (int)(int16_t)(w & 0xffff);
+        if constexpr (MET == MET_F16) { d0 >>= 11; d1 >>= 11; }
+    } else {
+        const float* p = reinterpret_cast<const float*>(raw + 8 * rel_stage);          // viterbiBM.cuh:146-153
+        f0 = fminf(fmaxf(p[0], -8.0f), 7.0f);
+        f1 = fminf(fmaxf(p[1], -8.0f), 7.0f);
+    }
+}
+
+template <int MET, int IN, int P>
+VIT_HD void build_step(const uint8_t* raw, int rel_stage, uint32_t* entry /* 8 words: class-major */) {
+    using C = Core<MET, IN>;
+    int d0, d1; float f0, f1;
+    load_symbols<MET, IN>(raw, rel_stage, d0, d1, f0, f1);
+    int A, B;
+    if constexpr (IN == IN_F32) {
+        A = (int)(f0 + f1); B = (int)(f0 - f1);                     // truncation is odd-symmetric
+    } else if constexpr (IN == IN_HARD) {
+        A = (d0 + d1) >> 1; B = (d0 - d1) >> 1;
+    } else {
+        A = d0 + d1; B = d0 - d1;
+    }
+    // class (c0,c1): D0 = c0 ? d0 : -d0, D1 = c1 ? d1 : -d1;  X = D0+D1, Y = D0-D1
+    //   cl 3: ( A,  B)   cl 2: ( B,  A)   cl 1: (-B, -A)   cl 0: (-A, -B)
+    const int X[4] = {-A, -B, B, A};
+    const int Y[4] = {-B, -A, A, B};
+    constexpr int HV = half_variant(P);
+#pragma unroll
+    for (int cl = 0; cl < 4; cl++) {
+        uint32_t w0, w1;
+        if constexpr (C::PACKED) {
+            // high half: (0) same, (3) negated, (1) X<->Y, (2) X->-Y, Y->-X
+            int xh = HV == 0 ? X[cl] : HV == 3 ? -X[cl] : HV == 1 ? Y[cl] : -Y[cl];
+            int yh = HV == 0 ? Y[cl] : HV == 3 ? -Y[cl] : HV == 1 ? X[cl] : -X[cl];
+            w0 = C::enc(X[cl]) | (C::enc(xh) << 16);
+            w1 = C::enc(Y[cl]) | (C::enc(yh) << 16);
+        } else {
+            w0 = C::enc(X[cl]); w1 = C::enc(Y[cl]);
+        }
+        entry[2 * cl] = w0; entry[2 * cl + 1] = w1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the warp body
+// ------------------------------------------------------------------------------------------------
+template <int MET, int IN, int BPP>
+struct WarpCtx {
+    LaneState<MET> st;
+    uint8_t* smem;
+    int lane, g, l;
+    uint32_t bm_off[6];        // byte offset of this lane's class entry within a stage row, per phase
+    uint32_t lane_field[3];    // phases 1,3,5
+    // segment geometry
+    unsigned long long seg_byte0;   // byte offset of the segment's first stage in the stream
+    const uint8_t* in;
+    uint8_t* out;
+    unsigned long long in_bytes;
+    unsigned long long out_word0;   // first decoded pack of this segment
+    unsigned seg_bits;              // L
+    unsigned t0;                    // absolute stage index of the current superchunk's stage 0
+};
+
+template <int MET, int IN, int BPP>
+VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP>& c, unsigned super_idx, int buf) {
+    using S = Smem<IN>;
+    constexpr int B96 = InTraits<IN>::B96;
+    unsigned long long b0 = c.seg_byte0 + (unsigned long long)super_idx * B96;
+    unsigned long long al = b0 & ~15ull;
+    uint8_t* dst = c.smem + S::OFF_RAW + (buf * SEGS_PER_WARP + c.g) * S::RAW_SEG;
+#pragma unroll
+    for (int i = 0; i < (raw_pieces<IN>() + 7) / 8; i++) {
+        int piece = c.l + 8 * i;
+        if (piece < raw_pieces<IN>()) {
+            unsigned long long off = al + 16ull * piece;
+            unsigned valid = off >= c.in_bytes ? 0u : (c.in_bytes - off >= 16 ? 16u : (unsigned)(c.in_bytes - off));
+            const uint8_t* src = c.in + (valid ? off : 0);
+            cp_async16(dst + 16 * piece, src, valid);
+        }
+    }
+    cp_async_commit();
+}
+
+template <int MET, int IN, int BPP, int P>
+VIT_HD void build_phase(WarpCtx<MET, IN, BPP>& c, int half, int buf, unsigned skew) {
+    using S = Smem<IN>;
+    const uint8_t* raw = c.smem + S::OFF_RAW + (buf * SEGS_PER_WARP + c.g) * S::RAW_SEG + skew;
+    int srel = half * CHUNK + P + 6 * c.l;       // stage within superchunk
+    uint32_t e[8];
+    build_step<MET, IN, P>(raw, srel, e);
+    uint32_t* row = reinterpret_cast<uint32_t*>(c.smem + S::OFF_BM + ((P + 6 * c.l) * SEGS_PER_WARP + c.g) * 32);
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(row)[0] = make_uint4(e[0], e[1], e[2], e[3]);
+    reinterpret_cast<uint4*>(row)[1] = make_uint4(e[4], e[5], e[6], e[7]);
+#else
+    for (int i = 0; i < 8; i++) row[i] = e[i];
+#endif
+}
+
+template <int MET, int IN, int BPP>
+VIT_HD void build_table(WarpCtx<MET, IN, BPP>& c, int half, int buf, unsigned skew) {
+    build_phase<MET, IN, BPP, 0>(c, half, buf, skew);
+    build_phase<MET, IN, BPP, 1>(c, half, buf, skew);
+    build_phase<MET, IN, BPP, 2>(c, half, buf, skew);
+    build_phase<MET, IN, BPP, 3>(c, half, buf, skew);
+    build_phase<MET, IN, BPP, 4>(c, half, buf, skew);
+    build_phase<MET, IN, BPP, 5>(c, half, buf, skew);
+}
+
+// subtract the segment-wide minimum metric (a common offset never changes a decision; the
+// reference does the same on a threshold, viterbiACS.cuh:307-378)
+template <int MET, int IN>
+VIT_HD void normalize(LaneState<MET>& s) {
+    using C = Core<MET, IN>;
+    uint32_t m = s.pm[0];
+#pragma unroll
+    for (int r = 1; r < LaneState<MET>::NPM; r++) m = C::vmin(m, s.pm[r]);
+    if constexpr (C::PACKED) m = C::vmin(m, prmt(m, 0, 0x1032));
+    m = C::vmin(m, shfl_xor(m, 1));
+    m = C::vmin(m, shfl_xor(m, 2));
+    m = C::vmin(m, shfl_xor(m, 4));
+#pragma unroll
+    for (int r = 0; r < LaneState<MET>::NPM; r++) s.pm[r] = C::sub(s.pm[r], m);
+}
+
+// stages per normalization (must divide 96 and be a multiple of 32)
+template <int MET, int IN> constexpr int norm_period() {
+    return (MET == MET_B16 && IN == IN_S8) ? 32 : (MET == MET_F16 && (IN == IN_S8 || IN == IN_S16)) ? 32 : 96;
+}
+
+// end of a 32-stage slide at superchunk stage S (S % 32 == 31): flush the register-exchange words
+// to ring slot S/32, trace back from state 0, emit one 32-bit word of decoded bits.
+template <int MET, int IN, int BPP, int S>
+VIT_HD void slide_end(WarpCtx<MET, IN, BPP>& c) {
+    using SM = Smem<IN>;
+    constexpr int SLOT = S / 32;
+    constexpr int P = S % 6;                      // phase of stage e (1, 3 or 5)
+    constexpr int LUTV = SLOT;                    // lut variant: word at e-32 has phase (P+4)%6
+    uint32_t* ring = reinterpret_cast<uint32_t*>(c.smem + SM::OFF_RING);
+    uint32_t* mine = ring + (SLOT * SEGS_PER_WARP + c.g) * 64 + c.l * 8;
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(mine)[0] = make_uint4(c.st.pp[0], c.st.pp[1], c.st.pp[2], c.st.pp[3]);
+    reinterpret_cast<uint4*>(mine)[1] = make_uint4(c.st.pp[4], c.st.pp[5], c.st.pp[6], c.st.pp[7]);
+#else
+    for (int k = 0; k < 8; k++) mine[k] = c.st.pp[k];
+#endif
+    // state 0 sits at position 0 in every phase: lane 0 of the group, register 0
+    uint32_t w_e = shfl_idx(c.st.pp[0], c.g * 8);
+    syncwarp();
+    const unsigned e = c.t0 + S;
+    if (e >= 95) {
+        unsigned st1 = brev32(w_e) & 63u;                                   // reference viterbiTB.cuh:9-12
+        const uint8_t* lut = c.smem + SM::OFF_LUT + LUTV * 64;
+        unsigned idx = lut[st1];
+        uint32_t word = ring[(((SLOT + 2) % 3) * SEGS_PER_WARP + c.g) * 64 + idx];   // viterbiTB.cuh:14-19
+        unsigned k = (e - 95) / 32;                                         // slide index
+        if (c.l == 0) {
+            if constexpr (BPP == 32) {
+                if (k * 32 < c.seg_bits) reinterpret_cast<uint32_t*>(c.out)[c.out_word0 + k] = word;
+            } else {
+                uint16_t* o = reinterpret_cast<uint16_t*>(c.out) + c.out_word0 + 2ull * k;
+                if (k * 32 < c.seg_bits) o[0] = (uint16_t)(word >> 16);
+                if (k * 32 + 16 < c.seg_bits) o[1] = (uint16_t)(word & 0xffff);
+            }
+        }
+    }
+    // start the next word: message bits e-5..e are the state index
+    insert_field<MET, P, 26, 6, true>(c.st, c.lane_field[P / 2]);
+}
+
+template <int MET, int IN, int BPP, int S>
+VIT_HD void one_stage(WarpCtx<MET, IN, BPP>& c) {
+    using SM = Smem<IN>;
+    constexpr int P = S % 6;
+    const uint32_t* ent = reinterpret_cast<const uint32_t*>(c.smem + SM::OFF_BM + (S % CHUNK) * (SEGS_PER_WARP * 32) + c.bm_off[P]);
+#if defined(__CUDA_ARCH__)
+    uint2 w = *reinterpret_cast<const uint2*>(ent);
+    acs_stage<MET, IN, P>(c.st, w.x, w.y);
+#else
+    acs_stage<MET, IN, P>(c.st, ent[0], ent[1]);
+#endif
+    constexpr int V = S % 32;
+    if constexpr (V == 31) slide_end<MET, IN, BPP, S>(c);
+    else if constexpr (V == 5) insert_field<MET, P, 20, 6, false>(c.st, c.lane_field[P / 2]);
+    else if constexpr (V == 11) insert_field<MET, P, 14, 6, false>(c.st, c.lane_field[P / 2]);
+    else if constexpr (V == 17) insert_field<MET, P, 8, 6, false>(c.st, c.lane_field[P / 2]);
+    else if constexpr (V == 23) insert_field<MET, P, 2, 6, false>(c.st, c.lane_field[P / 2]);
+    else if constexpr (V == 29) insert_field<MET, P, 0, 2, false>(c.st, c.lane_field[P / 2]);
+}
+
+template <int MET, int IN, int BPP, int S0, int S1>
+struct StageRange {
+    static VIT_HD void run(WarpCtx<MET, IN, BPP>& c) {
+        one_stage<MET, IN, BPP, S0>(c);
+        StageRange<MET, IN, BPP, S0 + 1, S1>::run(c);
+    }
+};
+template <int MET, int IN, int BPP, int S1>
+struct StageRange<MET, IN, BPP, S1, S1> {
+    static VIT_HD void run(WarpCtx<MET, IN, BPP>&) {}
+};
+
+// Decode the 4 segments owned by warp `warp_id` of stream `stream`.
+template <int MET, int IN, int BPP>
+VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int lane, uint8_t* smem) {
+    using SM = Smem<IN>;
+    WarpCtx<MET, IN, BPP> c;
+    c.smem = smem; c.lane = lane; c.g = lane >> 3; c.l = lane & 7;
+
+    // segment partition, reference viterbi.cu:156-165
+    const unsigned W = kp.segments;
+    const unsigned long long q = kp.packs / W, rem = kp.packs % W;
+    const unsigned long long w = (unsigned long long)warp_id * SEGS_PER_WARP + c.g;
+    unsigned long long Lp = (w < W) ? q + (w < rem ? 1 : 0) : 0;
+    const unsigned long long start_pack = q * w + (w < rem ? w : rem);
+    c.seg_bits = (unsigned)(Lp * BPP);
+    c.out_word0 = start_pack;
+    const unsigned long long s0 = start_pack * BPP;                       // first message index
+    c.seg_byte0 = s0 * InTraits<IN>::B96 / 96;
+    c.in = kp.in + (unsigned long long)stream * kp.in_stride;
+    c.out = kp.out + (unsigned long long)stream * kp.out_stride;
+    c.in_bytes = kp.in_bytes;
+
+    // the first segment of the warp is never shorter than the others
+    const unsigned long long w_first = (unsigned long long)warp_id * SEGS_PER_WARP;
+    const unsigned long long Lp_first = (w_first < W) ? q + (w_first < rem ? 1 : 0) : 0;
+    if (Lp_first == 0) return;
+    const unsigned Lmax = (unsigned)(Lp_first * BPP);
+    const unsigned Tmax = 64 + 32 * ((Lmax + 31) / 32);                   // viterbi.cu:176-197
+    const unsigned nsuper = (Tmax + SUPER - 1) / SUPER;
+
+#pragma unroll
+    for (int p = 0; p < 6; p++) c.bm_off[p] = (uint32_t)(c.g * 32 + lane_class_of(c.l, p) * 8);
+#pragma unroll
+    for (int i = 0; i < 3; i++) c.lane_field[i] = lane_field_of(c.l, 2 * i + 1);
+#pragma unroll
+    for (int r = 0; r < LaneState<MET>::NPM; r++) c.st.pm[r] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c.st.pp[k] = 0;
+
+    // traceback lookup: variant v (ring slot of e) -> position of a state at phase of stage e-32
+    {
+        uint8_t* lut = smem + SM::OFF_LUT;
+        for (int i = lane; i < 3 * 64; i += 32) {
+            int v = i / 64, st = i % 64;
+            int pw = mod6((v * 32 + 31) + 4);                           // phase of stage e-32
+            lut[i] = (uint8_t)pos_index_of_state(st, pw);
+        }
+    }
+
+    issue_raw_copy(c, 0, 0);
+    for (unsigned sc = 0; sc < nsuper; sc++) {
+        const int buf = (int)(sc & 1);
+        c.t0 = sc * SUPER;
+        const unsigned skew = (unsigned)((c.seg_byte0 + (unsigned long long)sc * InTraits<IN>::B96) & 15ull);
+        if (sc + 1 < nsuper) { issue_raw_copy(c, sc + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        syncwarp();
+
+        normalize<MET, IN>(c.st);
+        build_table(c, 0, buf, skew);
+        syncwarp();
+        StageRange<MET, IN, BPP, 0, 32>::run(c);
+        if constexpr (norm_period<MET, IN>() == 32) normalize<MET, IN>(c.st);
+        if (c.t0 + 32 >= Tmax) break;
+        StageRange<MET, IN, BPP, 32, 48>::run(c);
+        syncwarp();
+        build_table(c, 1, buf, skew);
+        syncwarp();
+        StageRange<MET, IN, BPP, 48, 64>::run(c);
+        if constexpr (norm_period<MET, IN>() == 32) normalize<MET, IN>(c.st);
+        if (c.t0 + 64 >= Tmax) break;
+        StageRange<MET, IN, BPP, 64, 96>::run(c);
+        syncwarp();
+    }
+}
+
+#if defined(__CUDACC__)
+template <int MET, int IN, int BPP>
+__global__ void __launch_bounds__(32) vit_decode_kernel(const KParams kp) {
+    extern __shared__ __align__(16) uint8_t vit_smem[];
+    warp_body<MET, IN, BPP>(kp, blockIdx.x, blockIdx.y, (int)threadIdx.x, vit_smem);
+}
+#endif
+
+}  // namespace vitk

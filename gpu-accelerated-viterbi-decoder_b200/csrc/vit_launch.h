@@ -1,0 +1,19 @@
+// vit_launch.h -- internal: one launcher per (metric core, input type, output pack) kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include "vit_kernel.cuh"
+
+namespace vitk {
+struct KernelEntry {
+    cudaError_t (*launch)(const KParams& kp, dim3 grid, cudaStream_t stream);
+    const void* func;
+    int smem_bytes;
+};
+// met: MET_*, in: IN_*, bpp16: 0/1.  Returns nullptr for combinations that are not built.
+const KernelEntry* kernel_entry(int met, int in, int bpp16);
+
+// defined by the instantiation units
+const KernelEntry* kernel_entry_b32(int in, int bpp16);
+const KernelEntry* kernel_entry_b16(int in, int bpp16);
+const KernelEntry* kernel_entry_f16(int in, int bpp16);
+}  // namespace vitk

@@ -1,0 +1,95 @@
+/*
+ * vit_b200.h -- C ABI of the B200-native Viterbi decoder (libvitb200.so).
+ *
+ * Drop-in boundary for the reference's host class `template<int options> class ViterbiCUDA`
+ * (reference src/viterbi/viterbi.h:91-152, implemented in src/viterbi/viterbi.cu:10-139,210-238)
+ * as consumed by ViterbiDecoder<options>::process (src/viterbiDF.h:186-196) and runPipeline
+ * (src/main.cpp:119-138).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * `options` is the reference's bitfield (viterbi.h:7-20):
+ *   bits 0-3  ChannelIn : HARD=0 SOFT4=1 SOFT8=2 SOFT16=3 FP32=4
+ *   bits 4-7  Metric    : B32=0x00 B16=0x10 FP16=0x20
+ *   bits 8-11 DecodeOut : O_B32=0x000 O_B16=0x100
+ *   bits 12-15 CompMode : REG=0x0000 DPX=0x1000 (both select the same core, as in the reference
+ *                         where the flag is never forwarded: viterbi.cu:181,192,204)
+ * Every size argument called `inputNum` is the number of CODED SYMBOLS (2 x message bits), exactly
+ * as in the reference (viterbi.cu:63-92,210-215).
+ *
+ * All functions returning int return 0 on success and a non-zero code on failure;
+ * vit_last_error() then describes the failure (thread local).  Nothing here prints or exits: the
+ * C++ shim (host/viterbi.h) turns a failure into the reference's "print + exit(EXIT_FAILURE)"
+ * convention (reference src/viterbi/gpuerrors.h:8-17).
+ */
+#ifndef VIT_B200_H
+#define VIT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vit_handle vit_handle;
+
+enum {
+    VIT_OK = 0,
+    VIT_ERR_OPTIONS = 1,   /* option combination not supported */
+    VIT_ERR_CUDA = 2,      /* a CUDA runtime call failed */
+    VIT_ERR_ARG = 3        /* bad pointer / alignment / size */
+};
+
+/* replaces ViterbiCUDA<options>::ViterbiCUDA() and ViterbiCUDA(size_t inputNum)
+ * (viterbi.cu:23-36).  prealloc_inputNum > 0 sizes the device buffers up front; they grow on
+ * demand otherwise.  `device` is the CUDA ordinal (the reference hard-codes 0, viterbi.cu:134). */
+int vit_create(vit_handle** out, int options, int device, size_t prealloc_inputNum);
+
+/* replaces ~ViterbiCUDA (viterbi.cu:38-42) */
+void vit_destroy(vit_handle* h);
+
+/* replaces ViterbiCUDA<options>::run(input_h, output_h, inputNum, kernelTime) (viterbi.cu:210-238):
+ * host buffers in and out, synchronous.  in_h holds vit_input_size() bytes, out_h receives
+ * vit_output_size() bytes.  kernel_ms (optional) = device time of the decode kernel in ms,
+ * measured with CUDA events around the launch only, as the reference does (viterbi.cu:224-232). */
+int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float* kernel_ms);
+
+/* device-resident variant (no copies): in_d must be 16-byte aligned and hold vit_input_size()
+ * bytes; out_d receives vit_output_size() bytes.  cuda_stream is a cudaStream_t (NULL = default
+ * stream).  Asynchronous unless kernel_ms is non-NULL.  New relative to the reference: needed for
+ * device-generated input and multi-GPU stream sharding. */
+int vit_run_device(vit_handle* h, const void* in_d, void* out_d, size_t inputNum,
+                   void* cuda_stream, float* kernel_ms);
+
+/* nstreams independent codeword streams of inputNum symbols each, one launch.  Stream s lives at
+ * in_d + s*in_stride (16-byte multiple) and decodes to out_d + s*out_stride. */
+int vit_run_device_batch(vit_handle* h, const void* in_d, void* out_d, size_t inputNum,
+                         size_t nstreams, size_t in_stride, size_t out_stride,
+                         void* cuda_stream, float* kernel_ms);
+
+/* replace getInputSize / getMessageLen / getOutputSize (viterbi.cu:63-92); bytes, bits, bytes */
+size_t vit_input_size(int options, size_t inputNum);
+size_t vit_message_len(int options, size_t inputNum);
+size_t vit_output_size(int options, size_t inputNum);
+
+/* 1 if this library decodes the combination.  Superset of the reference's OptionsValid
+ * (viterbi.h:22-36): FP16 metric with SOFT8/SOFT16 input is accepted (symbols are pre-scaled to
+ * 5 bits); B16 metric with SOFT16 input is rejected as in the reference. */
+int vit_options_valid(int options);
+/* exactly the reference's OptionsValid<options>::value */
+int vit_options_valid_ref(int options);
+
+/* static kernel facts for reporting: registers per thread, dynamic shared memory per block,
+ * threads per block, stream segments per block.  Returns non-zero if the kernel is missing. */
+int vit_kernel_info(int options, int* regs, int* smem_bytes, int* block_threads, int* segs_per_block);
+
+/* launches issued by this handle so far (one decode kernel per run) */
+unsigned long long vit_launch_count(const vit_handle* h);
+
+/* test hook: number of stream segments (reference: 6400, viterbi.cu:19); 0 restores 6400 */
+int vit_set_segments(vit_handle* h, unsigned segments);
+
+const char* vit_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -53,6 +53,7 @@ def lib():
         L.vo_count_errors.restype = C.c_uint64
         L.vo_count_errors.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p]
         L.vo_num_threads.restype = C.c_int
+        L.vo_set_segments.restype, L.vo_set_segments.argtypes = None, [sz]
         _lib = L
     return _lib
 
@@ -113,7 +114,9 @@ def pack(input_type, soft, scale=1.0):
         out = np.empty(n, np.float32)
     else:
         per = {HARD: 32, SOFT4: 8, SOFT8: 4, SOFT16: 2}[input_type]
-        assert n % per == 0, "symbol count must fill whole int32 packs"
+        if n % per:  # fill the last int32 pack with zero-valued symbols
+            soft = np.concatenate([soft, np.zeros(per - n % per, np.float32)])
+            n = soft.size
         out = np.empty(n // per, np.int32)
     lib().vo_pack(input_type, _ptr(soft), n, scale, _ptr(out))
     return out
@@ -129,6 +132,11 @@ def count_errors(options, out, message_len_, bits):
     out = np.ascontiguousarray(out)
     bits = np.ascontiguousarray(bits, np.uint8)
     return int(lib().vo_count_errors(options, _ptr(out), message_len_, _ptr(bits)))
+
+
+def set_segments(w):
+    """test hook: segment count used by decode/overrun_words (0 -> the reference's 6400)."""
+    lib().vo_set_segments(w)
 
 
 def num_threads():
@@ -147,6 +155,55 @@ def make_channel(n_bits, input_type, snr_db=None, seed=1, scale=40000.0, prbs=Fa
     if sigma:
         soft = soft + rng.standard_normal(soft.size, dtype=np.float32) * np.float32(sigma)
     return bits, pack(input_type, soft, scale), 2 * n_bits
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def make_channel_det(n_bits, input_type, seed=1, amp=None, sigma=0.0, zero=False):
+    """Bit-reproducible channel (integer arithmetic only, no libm, no numpy RNG): PRBS-31 message,
+    K=7 encoder, symbol = +-amp + noise in Q8 fixed point, noise = (sum of four 16-bit uniforms from
+    splitmix64, centred) scaled to a standard deviation of about sigma*amp, then the reference's
+    quantise/clamp and MSB-first packing (viterbiDF.h:105-166).  Used for the golden vectors.
+    Returns (bits, packed, input_num)."""
+    if amp is None:
+        amp = {HARD: 64, SOFT4: 3, SOFT8: 40, SOFT16: 9000, FP32: 48}[input_type]
+    bits = prbs31(0x7FFFFFFF ^ seed, n_bits)
+    coded = encode(bits).astype(np.int64)
+    per = {HARD: 32, SOFT4: 8, SOFT8: 4, SOFT16: 2, FP32: 1}[input_type]
+    nsym = coded.size
+    v = (2 * coded - 1) * (amp << 8)
+    sigma_q16 = int(round(sigma * amp * 256 / 0.57735))
+    if sigma_q16:
+        with np.errstate(over="ignore"):
+            h = _splitmix64(np.arange(nsym, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x100000001B3))
+        u = ((h & np.uint64(0xFFFF)) + ((h >> np.uint64(16)) & np.uint64(0xFFFF)) +
+             ((h >> np.uint64(32)) & np.uint64(0xFFFF)) + (h >> np.uint64(48))).astype(np.int64) - 2 * 65535
+        v = v + ((u * sigma_q16) >> 16)
+    v = v >> 8
+    if zero:
+        v = np.zeros_like(v)
+    if input_type == FP32:
+        return bits, (v.astype(np.float32) / np.float32(16.0)), 2 * n_bits
+    if nsym % per:
+        v = np.concatenate([v, np.zeros(per - nsym % per, np.int64)])
+    if input_type == HARD:
+        q = (v > 0).astype(np.uint32)
+        width = 1
+    else:
+        width = {SOFT4: 4, SOFT8: 8, SOFT16: 16}[input_type]
+        lo, hi = -(1 << (width - 1)), (1 << (width - 1)) - 1
+        q = (np.clip(v, lo, hi) & ((1 << width) - 1)).astype(np.uint32)
+    q = q.reshape(-1, per)
+    word = np.zeros(q.shape[0], np.uint32)
+    for j in range(per):
+        word = (word << np.uint32(width)) | q[:, j] if width < 32 else q[:, j]
+    return bits, word.view(np.int32), 2 * n_bits
 
 
 # ---------------------------------------------------------------------------------------------

@@ -161,9 +161,12 @@ typedef struct {
     uint8_t* overrun_valid;
 } dec_ctx;
 
+static size_t g_segments = VO_SEGMENTS;   /* test hook: vo_set_segments */
+void vo_set_segments(size_t w) { g_segments = w ? w : VO_SEGMENTS; }
+
 static inline void seg_range(size_t P, int bpp, size_t w, size_t* s0, size_t* L) {
     /* viterbi.cu:156-162 */
-    size_t q = P / VO_SEGMENTS, r = P % VO_SEGMENTS;
+    size_t q = P / g_segments, r = P % g_segments;
     *L = (q + (w < r ? 1 : 0)) * (size_t)bpp;
     *s0 = (q * w + (w < r ? w : r)) * (size_t)bpp;
 }
@@ -281,10 +284,10 @@ int vo_decode_segments(int options, const void* in, void* out, size_t inputNum,
     c.M = vo_message_len(options, inputNum);
     c.P = c.M / (size_t)bits_per_pack(options);
     c.overrun = NULL; c.overrun_valid = NULL;
-    if (seg_end > VO_SEGMENTS) seg_end = VO_SEGMENTS;
+    if (seg_end > g_segments) seg_end = g_segments;
     if (flags & VO_FLAG_REF_OVERRUN) {
-        c.overrun = (uint32_t*)calloc(2 * VO_SEGMENTS, sizeof(uint32_t));
-        c.overrun_valid = (uint8_t*)calloc(2 * VO_SEGMENTS, 1);
+        c.overrun = (uint32_t*)calloc(2 * g_segments, sizeof(uint32_t));
+        c.overrun_valid = (uint8_t*)calloc(2 * g_segments, 1);
     }
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
@@ -307,14 +310,14 @@ int vo_decode_segments(int options, const void* in, void* out, size_t inputNum,
 }
 
 int vo_decode(int options, const void* in, void* out, size_t inputNum, int nthreads, int flags) {
-    return vo_decode_segments(options, in, out, inputNum, 0, VO_SEGMENTS, nthreads, flags);
+    return vo_decode_segments(options, in, out, inputNum, 0, g_segments, nthreads, flags);
 }
 
 size_t vo_overrun_words(int options, size_t inputNum, uint64_t* idx, size_t cap) {
     int bpp = bits_per_pack(options);
     size_t P = vo_message_len(options, inputNum) / (size_t)bpp, cnt = 0;
     if (bpp != 16) return 0;
-    for (size_t w = 0; w < VO_SEGMENTS; w++) {
+    for (size_t w = 0; w < g_segments; w++) {
         size_t s0, L;
         seg_range(P, bpp, w, &s0, &L);
         if (L == 0 || L % 32 == 0) continue;

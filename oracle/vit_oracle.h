@@ -49,6 +49,8 @@ size_t vo_output_size(int options, size_t inputNum);
 
 /* number of stream segments, reference viterbi.cu:19 (blocksNum_total = 16*400) */
 #define VO_SEGMENTS 6400
+/* test hook: decode with a different segment count (0 restores 6400); not thread safe */
+void vo_set_segments(size_t w);
 
 /*
  * Decode `inputNum` coded symbols (packed as the reference's encPack_t stream for the option's input

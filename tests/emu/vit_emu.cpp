@@ -1,0 +1,125 @@
+// vit_emu.cpp -- host SIMT emulator for the product kernel source (TEST SCAFFOLDING ONLY).
+//
+// Compiles gpu-accelerated-viterbi-decoder_b200/csrc/vit_kernel.cuh with a plain host compiler and
+// runs each warp as 32 ucontext fibers in lockstep (every shuffle / syncwarp is a round-robin yield),
+// so the kernel's trellis mapping, operand tables, survivor-field insertion and traceback can be
+// checked against the oracle in the GPU-less authoring container.  It is never part of the product
+// library: the product path has no CPU fallback.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <ucontext.h>
+
+#include "../../gpu-accelerated-viterbi-decoder_b200/csrc/vit_kernel.cuh"
+
+namespace {
+constexpr int NL = 32;
+ucontext_t g_ctx[NL], g_main;
+int g_cur = 0;
+uint32_t g_slot[2][NL];
+unsigned g_shfl_k[NL];
+char* g_stacks = nullptr;
+constexpr size_t STACK = 512 * 1024;
+
+void yield_next() {
+    int me = g_cur;
+    int nx = (me + 1) % NL;
+    g_cur = nx;
+    swapcontext(&g_ctx[me], &g_ctx[nx]);
+}
+}  // namespace
+
+namespace vitk {
+uint32_t emu_shfl_xor(uint32_t v, int m) {
+    int me = g_cur;
+    unsigned b = g_shfl_k[me]++ & 1;
+    g_slot[b][me] = v;
+    yield_next();
+    return g_slot[b][me ^ m];
+}
+uint32_t emu_shfl_idx(uint32_t v, int src) {
+    int me = g_cur;
+    unsigned b = g_shfl_k[me]++ & 1;
+    g_slot[b][me] = v;
+    yield_next();
+    return g_slot[b][src & 31];
+}
+void emu_syncwarp() { yield_next(); }
+}  // namespace vitk
+
+namespace {
+struct Job {
+    vitk::KParams kp;
+    unsigned warp, stream;
+    uint8_t* smem;
+    int met, in, bpp;
+};
+Job g_job;
+
+template <int MET, int IN, int BPP>
+void run_lane(int lane) { vitk::warp_body<MET, IN, BPP>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem); }
+
+template <int MET, int IN>
+void run_lane_bpp(int lane) {
+    if (g_job.bpp == 16) run_lane<MET, IN, 16>(lane); else run_lane<MET, IN, 32>(lane);
+}
+template <int MET>
+void run_lane_in(int lane) {
+    switch (g_job.in) {
+        case 0: run_lane_bpp<MET, 0>(lane); break;
+        case 1: run_lane_bpp<MET, 1>(lane); break;
+        case 2: run_lane_bpp<MET, 2>(lane); break;
+        case 3: if constexpr (MET != vitk::MET_B16) run_lane_bpp<MET, 3>(lane); break;
+        default: run_lane_bpp<MET, 4>(lane); break;
+    }
+}
+void fiber_main(int lane) {
+    switch (g_job.met) {
+        case vitk::MET_B32: run_lane_in<vitk::MET_B32>(lane); break;
+        case vitk::MET_B16: run_lane_in<vitk::MET_B16>(lane); break;
+        default: run_lane_in<vitk::MET_F16>(lane); break;
+    }
+    g_cur = (lane + 1) % NL;   // falls through uc_link to the next lane (or main after lane 31)
+}
+
+void run_warp() {
+    if (!g_stacks) g_stacks = (char*)malloc(STACK * NL);
+    for (int i = 0; i < NL; i++) {
+        getcontext(&g_ctx[i]);
+        g_ctx[i].uc_stack.ss_sp = g_stacks + STACK * i;
+        g_ctx[i].uc_stack.ss_size = STACK;
+        g_ctx[i].uc_link = (i == NL - 1) ? &g_main : &g_ctx[i + 1];
+        makecontext(&g_ctx[i], (void (*)())fiber_main, 1, i);
+        g_shfl_k[i] = 0;
+    }
+    g_cur = 0;
+    swapcontext(&g_main, &g_ctx[0]);
+}
+}  // namespace
+
+extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inputNum, unsigned segments,
+                              unsigned nstreams, size_t in_stride, size_t out_stride) {
+    int it = options & 0xf, mt = (options >> 4) & 0xf, bpp = ((options >> 8) & 0xf) ? 16 : 32;
+    if (it > 4 || mt > 2) return -1;
+    if (mt == 1 && it == 3) return -1;
+    size_t in_bytes = it == 0 ? (inputNum + 7) / 8 : it == 1 ? (inputNum + 1) / 2 : it == 2 ? inputNum : it == 3 ? inputNum * 2 : inputNum * 4;
+    if (inputNum / 2 < 64) return 0;
+    size_t M = (inputNum / 2 - 64) / bpp * bpp;
+    g_job.kp.in = (const uint8_t*)in; g_job.kp.out = (uint8_t*)out;
+    g_job.kp.in_stride = in_stride; g_job.kp.out_stride = out_stride;
+    g_job.kp.in_bytes = in_bytes; g_job.kp.packs = M / bpp;
+    g_job.kp.segments = segments; g_job.kp.nstreams = nstreams;
+    g_job.met = mt == 0 ? vitk::MET_B32 : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
+    g_job.in = it; g_job.bpp = bpp;
+    g_job.smem = (uint8_t*)aligned_alloc(128, 64 * 1024);
+    unsigned nwarps = (segments + 3) / 4;
+    for (unsigned s = 0; s < nstreams; s++)
+        for (unsigned w = 0; w < nwarps; w++) {
+            g_job.warp = w; g_job.stream = s;
+            memset(g_job.smem, 0xA5, 64 * 1024);   // catch reads of unwritten shared memory
+            run_warp();
+        }
+    free(g_job.smem);
+    return 0;
+}

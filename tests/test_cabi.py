@@ -1,0 +1,85 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports everything the header
+declares, and its pure helpers agree with the reference's formulas.  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from vit_testlib import PKG_DIR, ROOT
+
+HEADER = os.path.join(ROOT, "include", "vit_b200.h")
+LIB = os.path.join(PKG_DIR, "libvitb200.so")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vit_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for s in ("vit_create", "vit_destroy", "vit_run", "vit_run_device", "vit_run_device_batch",
+              "vit_input_size", "vit_message_len", "vit_output_size", "vit_options_valid", "vit_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "build it: python -c 'import __graft_entry__ as g; g.build()'"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    missing = [s for s in declared_symbols() if s not in exported]
+    assert not missing, missing
+    # and nothing but the C ABI leaks out
+    assert all(s.startswith("vit_") for s in exported), sorted(s for s in exported if not s.startswith("vit_"))[:5]
+
+
+def test_library_contains_sm100a_code():
+    out = subprocess.run(["cuobjdump", "--list-elf", LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_size_helpers_and_option_table(V, O):
+    L = V.lib()
+    for opt in range(0, 0x2000):
+        it, mt, ot, cm = opt & 0xF, (opt >> 4) & 0xF, (opt >> 8) & 0xF, (opt >> 12) & 0xF
+        known = it <= 4 and mt <= 2 and ot <= 1 and cm <= 1
+        if not known:
+            assert not L.vit_options_valid(opt)
+            continue
+        assert bool(L.vit_options_valid_ref(opt)) == bool(O.lib().vo_options_valid_ref(opt))
+        # ours: superset (f16 x s8/s16 allowed, any comp mode); b16 x s16 rejected as in the reference
+        assert bool(L.vit_options_valid(opt)) == (not (mt == 1 and it == 3))
+        for n in (0, 100, 128, 2_000_000, 12_345_679):
+            assert L.vit_input_size(opt, n) == O.input_size(opt & 0xFFF, n)
+            assert L.vit_message_len(opt, n) == O.message_len(opt & 0xFFF, n)
+            assert L.vit_output_size(opt, n) == O.output_size(opt & 0xFFF, n)
+
+
+def test_errors_are_reported_not_fatal(V):
+    L = V.lib()
+    h = C.c_void_p()
+    assert L.vit_create(C.byref(h), 0x013, 0, 0) == 1          # VIT_ERR_OPTIONS: b16 x s16
+    assert b"unsupported" in L.vit_last_error()
+    with pytest.raises(V.ViterbiError):
+        V.ViterbiCUDA(0x7)                                       # unknown input type
+
+
+def test_parse_options_matches_main_flags(V):
+    # reference main.cpp:211-254
+    assert V.parse_options() == 0
+    assert V.parse_options("s4", "b16", "b32") == 0x011
+    assert V.parse_options("SOFT8", "f16", "b16") == 0x122
+    assert V.parse_options("f", "b32", "b32", "dpx") == 0x1004
+
+
+def test_no_cpu_fallback_in_product_sources():
+    """The product path must not reach into oracle/ or the emulator."""
+    for dirpath, _, files in os.walk(PKG_DIR):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".cpp", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("oracle table", "") or f == "vit_kernel.cuh", (dirpath, f)
+                assert "libvitemu" not in txt

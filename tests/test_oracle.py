@@ -1,0 +1,134 @@
+"""CPU tests of the golden model (oracle/) -- sizes, segmentation, identity, tie rules, golden vectors."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from vit_golden_cases import CASES
+from vit_testlib import ALL_OPTS, GOLDEN
+
+
+
+def test_size_helpers_follow_reference_formulas(O):
+    # reference viterbi.cu:63-92
+    for n in (0, 1, 127, 128, 129, 200, 2_000_000, 64_000_000, 12_345_679, 8_000_000_000):
+        for opt in ALL_OPTS:
+            bpp = 16 if opt & 0x100 else 32
+            exp_in = {0: (n + 7) // 8, 1: (n + 1) // 2, 2: n, 3: 2 * n, 4: 4 * n}[opt & 0xF]
+            exp_m = ((n // 2 - 64) // bpp * bpp) if n // 2 >= 64 else 0
+            assert O.input_size(opt, n) == exp_in
+            assert O.message_len(opt, n) == exp_m
+            assert O.output_size(opt, n) == exp_m // 8
+
+
+def test_size_helpers_match_reference_library(O):
+    if O.ref_lib() is None:
+        pytest.skip("oracle/_ref/libvitref.so not built")
+    for opt in ALL_OPTS + [o | 0x1000 for o in ALL_OPTS]:
+        for n in (128, 1000, 2_000_000, 64_000_000, 12_345_678):
+            r = O.ref_sizes(opt, n)
+            if r is None:
+                assert not O.lib().vo_options_valid_ref(opt)
+                continue
+            assert r == (O.input_size(opt, n), O.message_len(opt, n), O.output_size(opt, n))
+
+
+def test_baseline_config_sizes(O):
+    # decoded lengths at the BASELINE configs
+    assert O.message_len(0x000, 2 * 1_000_000) == 999_936
+    assert O.message_len(0x011, 2 * 32_000_000) == 31_999_936
+    assert O.message_len(0x122, 2 * 256_000_000) == 255_999_936
+    assert O.message_len(0x004, 2 * 4_000_000_000) == 3_999_999_936
+
+
+@pytest.mark.parametrize("opt", ALL_OPTS)
+def test_noiseless_identity(O, opt):
+    it = opt & 0xF
+    bits, packed, N = O.make_channel_det(250_000, it, seed=3)
+    out = O.decode(opt, packed, N)
+    M = O.message_len(opt, N)
+    assert M > 0 and out.size * (16 if opt & 0x100 else 32) == M
+    assert O.count_errors(opt, out, M, bits) == 0
+
+
+def test_first_config_cpu_pipeline(O):
+    """BASELINE config 0: ./main -n 1000000 -s 5.5 -m b32 -i h, host pipeline + golden model, no GPU."""
+    bits, packed, N = O.make_channel(1_000_000, O.HARD, snr_db=5.5, seed=1)
+    out = O.decode(0x000, packed, N)
+    assert O.count_errors(0x000, out, O.message_len(0x000, N), bits) == 0
+
+
+def test_tie_rules_differ_between_cores(O):
+    """All-zero soft input: every add-compare-select is a tie, so the output is a pure function of
+    the per-core tie table.  int16 and int32 differ only at phase 0; half2 is the mirror."""
+    n = 64 + 32 * 40
+    packed = np.zeros(n * 2 // 8, np.int32)
+    O.set_segments(2)
+    try:
+        o32 = O.decode(O.SOFT4 | O.M_B32, packed, 2 * n)
+        o16 = O.decode(O.SOFT4 | O.M_B16, packed, 2 * n)
+        of = O.decode(O.SOFT4 | O.M_FP16, packed, 2 * n)
+    finally:
+        O.set_segments(0)
+    assert not np.array_equal(o32, o16)
+    assert not np.array_equal(o16, of)
+    # int16 core: x = !u everywhere -> the survivor of state 0 alternates deterministically
+    assert len({int(v) for v in o16}) <= 4
+
+
+def test_segments_are_independent(O):
+    """Decoding a subset of segments writes exactly those segments' words (viterbi.cu:156-165)."""
+    bits, packed, N = O.make_channel_det(6400 * 32 * 2 + 64 + 32 * 17, O.SOFT4, seed=5, sigma=0.8)
+    full = O.decode(0x011, packed, N)
+    part = O.decode(0x011, packed, N, segs=(100, 200))
+    P = O.message_len(0x011, N) // 32
+    q, r = divmod(P, 6400)
+    start = lambda w: q * w + min(w, r)
+    a, b = start(100), start(200)
+    assert np.array_equal(part[a:b], full[a:b])
+    assert not part[:a].any() and not part[b:].any()
+
+
+def test_o16_and_o32_decode_the_same_bits(O):
+    """The output pack width only changes the segment partition and the traceback hop size."""
+    bits, packed, N = O.make_channel_det(6400 * 32 + 64, O.SOFT8, seed=9, sigma=0.5)
+    a = O.decode(0x012, packed, N)
+    b = O.decode(0x112, packed, N)
+    assert O.count_errors(0x012, a, O.message_len(0x012, N), bits) == 0
+    assert O.count_errors(0x112, b, O.message_len(0x112, N), bits) == 0
+
+
+def test_overrun_word_list(O):
+    # 16-bit packs, odd pack count per segment -> two shared words per boundary
+    N = 2 * (6400 * 16 * 3 + 64)
+    ov = O.overrun_words(0x112, N)
+    assert ov.size == 2 * 6400 - 2          # the last segment's over-run falls outside the buffer
+    assert O.overrun_words(0x012, N).size == 0
+    N = 2 * 256_000_000                      # BASELINE config 3/5: the last 4 segments are odd
+    assert O.overrun_words(0x122, N).size == 6
+
+
+def test_b16_rejects_s16(O):
+    with pytest.raises(ValueError):
+        O.decode(0x013, np.zeros(1000, np.int32), 1000)
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="tests/golden/ref_vectors.npz not generated yet")
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_reference_golden_vectors(O, case):
+    """Pin: the golden model reproduces, word for word, what the reference's own CUDA decoder
+    produced on a B200 for these seeded inputs (tests/golden/make_golden.py)."""
+    name, opt, n, seed, sigma, zero = case
+    g = np.load(GOLDEN)
+    bits, packed, N = O.make_channel_det(n, opt & 0xF, seed=seed, sigma=sigma, zero=zero)
+    assert hashlib.sha256(packed.tobytes()).digest() == g[name + "/sha"].tobytes(), "input generator drifted"
+    ref = g[name + "/out"]
+    ov = O.overrun_words(opt, N).astype(np.int64)
+    owned = np.ones(ref.size, bool)
+    owned[ov] = False
+    got = O.decode(opt, packed, N)
+    assert np.array_equal(got[owned], ref[owned])
+    # on the words the reference leaves to its over-run store, the over-run emulation must agree
+    got_ov = O.decode(opt, packed, N, flags=O.FLAG_REF_OVERRUN)
+    assert np.array_equal(got_ov, ref)

@@ -1,0 +1,39 @@
+"""Shared helpers for the test-suite (imported by path: the name `tests` is not a unique package)."""
+import importlib.util
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "gpu-accelerated-viterbi-decoder_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_vectors.npz")
+
+ALL_OPTS = [it | mt | ot for it in range(5) for mt in (0x00, 0x10, 0x20) for ot in (0x000, 0x100)
+            if not (mt == 0x10 and it == 3)]
+
+
+def load_pkg():
+    """The product package (directory name has hyphens, so it is loaded by path)."""
+    name = "gpu_accelerated_viterbi_decoder_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG_DIR, "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def owned_mask(O, opt, N, nwords):
+    """False on the words the reference leaves to its O_B16 over-run store race."""
+    import numpy as np
+    m = np.ones(nwords, bool)
+    m[O.overrun_words(opt, N).astype(np.int64)] = False
+    return m
