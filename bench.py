@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- decoded Gb/s of the B200-native Viterbi decoder on BASELINE.json's configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one decode of one synthetic codeword stream (PRBS-free random bits -> K=7 0171/0133 encoder
+-> BPSK + AWGN, sigma = 10^(-snr/5) -> x40000 -> saturating quantiser -> MSB-first packing, i.e. the
+reference harness's channel, reference src/main.cpp:131-138) through the hot path.  Default workload
+= BASELINE.json configs[1]: 32,000,000 message bits, 4-bit soft input, int16x2 core, 32-bit packs.
+
+Printed JSON (rank 0, one line):
+  value     whole-job decoded Gb/s with inputs resident in HBM, CUDA events on the launch stream,
+            max over ranks.  For N > 1 every rank decodes its own streams (weak scaling, no stream is
+            split) and the packed output bits are all-gathered over NCCL inside the timed region.
+  e2e       the same metric through the reference-facing call ViterbiCUDA.run(host_in, host_out)
+            (C ABI vit_run) with pinned HOST buffers: H2D copy, kernel, D2H copy every step.
+  roofline  the kernel is issue-bound, not HBM-bound: achieved decoded Gb/s against the
+            ACS-op issue roofline N_SM*4*f_SM / (3|6 warp-instructions per decoded bit); roofline_hbm is
+            the algorithmic-bytes view against MEASURED_PEAKS.json.
+  cpu_baseline  the scalar C golden model (oracle/, "port") on the host cores, bounded sample.
+`--impl reference` times the reference's own CUDA decoder (oracle/_ref/libvitref.so, built from the
+unmodified reference sources for sm_100) through its own run(); if that library is absent it times the
+C golden model on the host cores instead.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (options, message bits, snr dB)                      BASELINE.json configs[...]
+    "s4_b16_o32_32M": (0x011, 32_000_000, 15.0),   # configs[1] (the headline: metric is quoted on this)
+    "hard_b32_o32_32M": (0x000, 32_000_000, 15.0),  # ./main with no flags
+    "hard_b32_o32_1M": (0x000, 1_000_000, 5.5),     # configs[0]
+    "s8_f16_o16_256M": (0x122, 256_000_000, 3.0),   # configs[2]
+    "s16_f16_o16_256M": (0x123, 256_000_000, 3.0),  # configs[2]
+    "f_b32_o32_4G": (0x004, 4_000_000_000, 15.0),   # configs[3]
+    "s8_b16_o32_256M": (0x012, 256_000_000, 15.0),  # configs[4] per-stream shape
+}
+BYTES_PER_BIT_IN = {0: 0.25, 1: 1.0, 2: 2.0, 3: 4.0, 4: 8.0}
+N_SM = 148
+
+
+def load_pkg():
+    name = "gpu_accelerated_viterbi_decoder_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "gpu-accelerated-viterbi-decoder_b200", "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic channel on the device (torch = plumbing; not part of the measured path)
+# ------------------------------------------------------------------------------------------------
+def make_stream_device(torch, n_bits, input_type, snr_db, seed, device):
+    """Returns (bits int8[n] on device, packed uint8 tensor on device, inputNum)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    bits = torch.randint(0, 2, (n_bits,), dtype=torch.int8, device=device, generator=g)
+    b = torch.cat([torch.zeros(6, dtype=torch.int8, device=device), bits])
+
+    def par(taps):  # encoder buffer bit t (6 = newest) at step i is bits[i-6+t]; viterbiDF.h:48-60
+        acc = torch.zeros(n_bits, dtype=torch.int8, device=device)
+        for t in taps:
+            acc ^= b[t:t + n_bits]
+        return acc
+    o0, o1 = par([0, 3, 4, 5, 6]), par([0, 1, 3, 4, 6])       # 0171, 0133
+    del b
+    sym = torch.stack([o0, o1], 1).reshape(-1).to(torch.float32) * 2 - 1
+    del o0, o1
+    sigma = 10.0 ** (-snr_db / 5.0)                             # main.cpp:135
+    chunk = 1 << 26
+    for s in range(0, sym.numel(), chunk):
+        sym[s:s + chunk] += torch.randn(min(chunk, sym.numel() - s), device=device, generator=g) * sigma
+    nsym = sym.numel()
+    if input_type == 4:
+        packed = (sym * 40000.0).contiguous().view(torch.uint8)
+    elif input_type == 0:
+        hard = (sym > 0).to(torch.uint8)
+        pad = (-nsym) % 32
+        if pad:
+            hard = torch.cat([hard, torch.zeros(pad, dtype=torch.uint8, device=device)])
+        w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=device)
+        by = (hard.view(-1, 8) * w).sum(1, dtype=torch.int32).to(torch.uint8)      # MSB-first bytes
+        packed = by.view(-1, 4).flip(1).contiguous().view(-1)                      # big-endian word -> LE memory
+    else:
+        width = {1: 4, 2: 8, 3: 16}[input_type]
+        lo, hi = -(1 << (width - 1)), (1 << (width - 1)) - 1
+        q = torch.clamp(torch.round(sym * 40000.0), lo, hi)                        # viterbiDF.h:107-124
+        per = 32 // width
+        pad = (-nsym) % per
+        if pad:
+            q = torch.cat([q, torch.zeros(pad, device=device)])
+        if width == 4:
+            qi = q.to(torch.int16) & 0xF
+            by = ((qi[0::2] << 4) | qi[1::2]).to(torch.uint8)
+            packed = by.view(-1, 4).flip(1).contiguous().view(-1)
+        elif width == 8:
+            packed = q.to(torch.int8).view(torch.uint8).view(-1, 4).flip(1).contiguous().view(-1)
+        else:
+            packed = q.to(torch.int16).view(-1, 2).flip(1).contiguous().view(torch.uint8).view(-1)
+    del sym
+    return bits, packed, 2 * n_bits
+
+
+def count_errors_device(torch, out_u8, bits, M, bpp):
+    """out bit j <-> message bit j+26 (main.cpp:153-169), computed on the device in chunks."""
+    errs = 0
+    wbytes = bpp // 8
+    words_total = M // bpp
+    step = 1 << 22
+    sh = torch.arange(bpp - 1, -1, -1, device=out_u8.device, dtype=torch.int64)
+    for w0 in range(0, words_total, step):
+        w1 = min(words_total, w0 + step)
+        raw = out_u8[w0 * wbytes:w1 * wbytes]
+        words = (raw.view(torch.int16).to(torch.int64) & 0xFFFF) if bpp == 16 else (raw.view(torch.int32).to(torch.int64) & 0xFFFFFFFF)
+        db = ((words.unsqueeze(1) >> sh) & 1).reshape(-1).to(torch.int8)
+        errs += int((db != bits[26 + w0 * bpp:26 + w1 * bpp]).sum().item())
+    return errs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+def cpu_baseline(options, n_bits, snr, budget_s=12.0):
+    """Golden model on the host cores: whole stream if it is small, else a prefix of segments."""
+    from oracle import oracle as O
+    n_cpu = min(n_bits, 32_000_000)
+    bits, packed, N = O.make_channel(n_cpu, options & 0xF, snr_db=snr, seed=5)
+    M = O.message_len(options, N)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        O.decode(options, packed, N)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or reps >= 20:
+            break
+    return {"value": M * reps / dt / 1e9, "unit": "Gb/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "%d x full decode of a %d-bit stream (same options), OpenMP over the 6400 segments" % (reps, n_cpu)}
+
+
+def run_reference(args, options, n_bits, snr):
+    """--impl reference: the reference's own CUDA decoder through its own run() (host buffers)."""
+    from oracle import oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = {"metric": "decoded Gb/s", "unit": "Gb/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "message_bits": n_bits, "options": "0x%03x" % options, "snr_db": snr}}
+    have_gpu = O.ref_lib() is not None and O.ref_lib().ref_device_count() > 0
+    if not have_gpu or not O.lib().vo_options_valid_ref(options):
+        cb = cpu_baseline(options, n_bits, snr, budget_s=20.0)
+        base.update({"value": cb["value"], "ms_per_step": None, "dtype": "int64", "cpu_baseline": cb, "gpu_launches": 0,
+                     "e2e": {"value": cb["value"], "unit": "Gb/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "note": "reference CUDA decoder unavailable for this combination: C golden model (port) on host cores"})
+        print(json.dumps(base))
+        return
+    bits, packed, N = O.make_channel(min(n_bits, 256_000_000), options & 0xF, snr_db=snr, seed=5)
+    M = O.message_len(options, N)
+    for _ in range(args.warmup):
+        O.ref_decode(options, packed, N)
+    kms, t0 = [], time.perf_counter()
+    with ClockSampler(0) as cs:
+        for _ in range(args.steps):
+            _, ms = O.ref_decode(options, packed, N)
+            kms.append(ms)
+    wall = time.perf_counter() - t0
+    base.update({
+        "value": M / (statistics.mean(kms) * 1e6), "ms_per_step": statistics.mean(kms), "dtype": "int16x2" if options & 0x10 else "int32",
+        "gpu_launches": args.steps, "clocks": cs.summary(),
+        "e2e": {"value": M * args.steps / wall / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": int(O.input_size(options, N)),
+                "d2h_bytes_per_step": int(O.output_size(options, N))},
+        "cpu_baseline": {"value": None, "unit": "Gb/s", "cores": 0, "kind": "reference",
+                         "sample": "reference CUDA decoder (oracle/_ref/libvitref.so, -arch=sm_100) on GPU 0; value = its own cudaEvent kernel time, "
+                                   "e2e = wall clock of ViterbiCUDA::run incl. its cudaMalloc/cudaMemcpy/cudaFree"},
+    })
+    print(json.dumps(base))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="s4_b16_o32_32M", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    options, n_bits, snr = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference(args, options, n_bits, snr)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    V = load_pkg()
+    it, bpp = options & 0xF, (16 if options & 0x100 else 32)
+    dec = V.ViterbiCUDA(options, 2 * n_bits, device=local)
+    N = 2 * n_bits
+    M = dec.getMessageLen(N)
+    in_bytes, out_bytes = dec.getInputSize(N), dec.getOutputSize(N)
+
+    # distinct input streams rotated step to step so that the working set exceeds L2 (126 MB)
+    nbuf = max(2, min(8, int(300e6 // in_bytes) + 1)) if in_bytes < 300e6 else 1
+    streams = []
+    for k in range(nbuf):
+        bits, packed, _ = make_stream_device(torch, n_bits, it, snr, 1000 * rank + k + 1, dev)
+        pad = (-packed.numel()) % 256
+        if pad:
+            packed = torch.cat([packed, torch.zeros(pad, dtype=torch.uint8, device=dev)])
+        streams.append((bits if k == 0 else None, packed))
+    d_out = torch.zeros((out_bytes + 255) // 256 * 256, dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(d_out) for _ in range(world)] if world > 1 else None
+    st = torch.cuda.current_stream()
+
+    def step(k):
+        dec.run_device(streams[k % nbuf][1].data_ptr(), d_out.data_ptr(), N, stream=st.cuda_stream)
+        if world > 1:
+            dist.all_gather(gathered, d_out)   # NCCL over NVLink: packed output bits only
+
+    # correctness gate inside the bench: BER == 0 at this SNR, and a slice equals the golden model
+    step(0)
+    torch.cuda.synchronize()
+    errs = count_errors_device(torch, d_out, streams[0][0], M, bpp)
+    check = {"bit_errors": errs, "ber": errs / M}
+    if rank == 0:
+        from oracle import oracle as O
+        host_in = streams[0][1][:in_bytes].cpu().numpy()
+        seg = O.decode(options, host_in, N, segs=(1000, 1016))
+        P = M // bpp
+        q, r = divmod(P, 6400)
+        a, b = q * 1000 + min(1000, r), q * 1016 + min(1016, r)
+        got = d_out[:out_bytes].cpu().numpy().view(np.uint16 if bpp == 16 else np.uint32)
+        check["oracle_slice_equal"] = bool(np.array_equal(got[a:b], seg[a:b]))
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = dec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as cs:
+        e0.record(st)
+        for k in range(args.steps):
+            step(k)
+        e1.record(st)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
+        # kernel-only duration for the roofline: events bracketing the launch on the launch stream
+        kms = []
+        for k in range(min(args.steps, 20)):
+            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), d_out.data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True))
+    launches = dec.launch_count() - launches0 - len(kms)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = M * world / (ms_step * 1e6)                       # whole-job decoded Gb/s
+    kernel_ms = statistics.mean(kms)
+
+    # e2e through the public host-buffer call (pinned host memory), copies inside the timed region
+    e2e = None
+    if not args.no_e2e and in_bytes < 8e9:
+        h_in = [s[1][:in_bytes].cpu().pin_memory() for s in streams[:min(nbuf, 4)]]
+        h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+        h_out_np = h_out.numpy().view(dec.decPack_t)
+        h_in_np = [h.numpy() for h in h_in]
+        for k in range(3):
+            dec.run(h_in_np[k % len(h_in_np)], N, output_h=h_out_np)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            dec.run(h_in_np[k % len(h_in_np)], N, output_h=h_out_np)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": M * world * args.steps / dt / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": int(in_bytes),
+               "d2h_bytes_per_step": int(out_bytes), "host_memory": "pinned", "timer": "host wall clock around the synchronous call"}
+
+    if rank == 0:
+        hbm_peak, sm_max_mhz, peak_kind = measured_peaks()
+        clocks = cs.summary()
+        f_mhz = clocks["sm_mhz"] or sm_max_mhz
+        wi_per_bit = 6 if (options & 0xF0) == 0 else 3          # int32 core 6, packed cores 3
+        issue_peak_nominal = N_SM * 4 * sm_max_mhz * 1e6 / wi_per_bit / 1e9
+        issue_peak_at_clock = N_SM * 4 * f_mhz * 1e6 / wi_per_bit / 1e9
+        k_gbps = M / (kernel_ms * 1e6)
+        alg_bytes = M * (BYTES_PER_BIT_IN[it] + 0.125)
+        info = dec.kernel_info()
+        line = {
+            "metric": "decoded Gb/s", "value": value, "unit": "Gb/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {0x00: "int32", 0x10: "int16x2", 0x20: "f16x2"}[options & 0xF0], "data": "synthetic",
+            "config": {"workload": args.workload, "message_bits": n_bits, "options": "0x%03x" % options, "snr_db": snr,
+                       "segments": 6400, "streams_per_step_per_gpu": 1, "l2": "inputs rotate over %d distinct device buffers (%.0f MB > 126 MB L2)" % (nbuf, nbuf * in_bytes / 1e6),
+                       "parallelism": "stream-sharded x%d, NCCL all_gather of packed output bits" % world if world > 1 else "single GPU"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
+            "kernel": {"ms": kernel_ms, "gbps": k_gbps, "regs": info["regs"], "smem_bytes": info["smem_bytes"],
+                       "grid": [1600, 1, 1], "block": 32},
+            "roofline": {"bound": "issue", "achieved": k_gbps, "peak": issue_peak_nominal, "unit": "Gb/s decoded", "frac": k_gbps / issue_peak_nominal,
+                         "peak_at_measured_clock": issue_peak_at_clock, "frac_at_measured_clock": k_gbps / issue_peak_at_clock,
+                         "how": "ACS-op roofline: 192 add/compare-select ops per decoded bit = %d warp-instructions; peak = 148 SM x 4 issue/clk x f_SM / that" % wi_per_bit,
+                         "traffic": None},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e6), "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / (kernel_ms * 1e6) / hbm_peak, "peak_kind": peak_kind, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg_bytes},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(options, n_bits, snr)
+        print(json.dumps(line))
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,200 @@
+// main.cpp -- bench harness with the reference ./main's flags and semantics
+// (reference src/main.cpp:14-264: -n/-s/-i/-m/-o/-c/-v/-h; sigma = 10^(-snr/5); quantiser scale 40000;
+// BER = mismatches / messageLen with decoded bit i compared to generated bit i+extraL).
+// Additions: reproducible seeds (--seed, --prbs), size_t message lengths, decoded Gb/s from device-side
+// kernel time, repeated timed runs (--reps) and multi-GPU stream sharding (--streams / --gpus: independent
+// codeword streams, one decoder per GPU, no stream is ever split).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "viterbiDF.h"
+
+struct Args {
+    size_t messageLen = 32000000;   // main.cpp:176
+    float snr = 15.0f;              // main.cpp:177
+    int options = 0;                // HARD | B32 | O_B32 | REG, main.cpp:178
+    bool verbose = false;
+    bool prbs = false;
+    long seed = -1;                 // < 0: std::random_device, as the reference (main.cpp:131-135)
+    int reps = 1;
+    int streams = 1;
+    int gpus = 1;
+};
+
+static void usage(const char* prog) {
+    std::cout << "Usage: " << prog << " [options]\n"
+              << "Options:\n"
+              << "  -n, --num <integer>      Set the message length.\n"
+              << "  -s, --snr <float>        Set the Signal-to-Noise Ratio (SNR).\n"
+              << "  -i, --input <type>       Set the input channel type (HARD|h, SOFT4|s4, SOFT8|s8, SOFT16|s16, FP32|f).\n"
+              << "  -m, --metric <type>      Set the metric type (b16, b32, f16).\n"
+              << "  -o, --output <type>      Set the output type (b16, b32).\n"
+              << "  -c, --compMode <type>    Set the computation mode (REG|reg, DPX|dpx).\n"
+              << "  -v, --verbose            Enable verbose output.\n"
+              << "      --seed <integer>     Fixed seed for bits (noise uses seed+1); default: random_device.\n"
+              << "      --prbs               PRBS-31 message bits instead of mt19937.\n"
+              << "      --reps <integer>     Timed decoder runs (best kernel time is reported).\n"
+              << "      --streams <integer>  Independent copies of the stream to decode (sharded over --gpus).\n"
+              << "      --gpus <integer>     Number of GPUs (one decoder and one host thread per GPU).\n"
+              << "  -h, --help               Display this help message.\n";
+}
+
+static int lookup(const std::string& flag, const std::string& v, std::initializer_list<std::pair<const char*, int>> table) {
+    for (const auto& kv : table) if (v == kv.first) return kv.second;
+    std::cerr << "Error: Invalid value '" << v << "' for " << flag << "." << std::endl;
+    std::exit(1);
+}
+
+static Args parseArg(int argc, char* argv[]) {
+    Args a;
+    for (int i = 1; i < argc; ++i) {
+        const std::string f = argv[i];
+        auto value = [&]() -> std::string {
+            if (i + 1 >= argc) { std::cerr << "Error: Unknown or incomplete argument: " << f << std::endl; std::exit(1); }
+            return argv[++i];
+        };
+        auto number = [&](auto conv) {
+            const std::string v = value();
+            try { return conv(v); }
+            catch (const std::exception&) { std::cerr << "Error: Invalid argument for " << f << "." << std::endl; std::exit(1); }
+        };
+        if (f == "-h" || f == "--help") { usage(argv[0]); std::exit(0); }
+        else if (f == "-n" || f == "--num") a.messageLen = number([](const std::string& s) { return static_cast<size_t>(std::stoull(s)); });
+        else if (f == "-s" || f == "--snr") a.snr = number([](const std::string& s) { return std::stof(s); });
+        // each field REPLACES its bits (the reference ORs, so repeating a flag corrupts options: main.cpp:224-232)
+        else if (f == "-m" || f == "--metric")
+            a.options = (a.options & ~METRIC_MASK) | lookup(f, value(), {{"b16", M_B16}, {"b32", M_B32}, {"f16", M_FP16}});
+        else if (f == "-i" || f == "--input")
+            a.options = (a.options & ~CHANNEL_MASK) | lookup(f, value(), {{"HARD", HARD}, {"h", HARD}, {"SOFT4", SOFT4}, {"s4", SOFT4},
+                        {"SOFT8", SOFT8}, {"s8", SOFT8}, {"SOFT16", SOFT16}, {"s16", SOFT16}, {"FP32", FP32}, {"f", FP32}});
+        else if (f == "-o" || f == "--output")
+            a.options = (a.options & ~DECODE_MASK) | lookup(f, value(), {{"b16", O_B16}, {"b32", O_B32}});
+        else if (f == "-c" || f == "--compMode")
+            a.options = (a.options & ~COMP_MASK) | lookup(f, value(), {{"REG", REG}, {"reg", REG}, {"DPX", DPX}, {"dpx", DPX}});
+        else if (f == "-v" || f == "--verbose") a.verbose = true;
+        else if (f == "--prbs") a.prbs = true;
+        else if (f == "--seed") a.seed = number([](const std::string& s) { return std::stol(s); });
+        else if (f == "--reps") a.reps = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
+        else if (f == "--streams") a.streams = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
+        else if (f == "--gpus") a.gpus = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
+        else { std::cerr << "Error: Unknown or incomplete argument: " << f << std::endl; std::exit(1); }
+    }
+    return a;
+}
+
+struct Outcome { size_t ben = 0, decoded = 0; double best_ms = 0, box_gbps = 0; };
+
+template <int options>
+Outcome runPipeline(const Args& a) {
+    using Dec = ViterbiCUDA<options>;
+    using decVec_t = typename ViterbiDecoder<options>::decVec_t;
+    constexpr int bitsPerPack = Dec::bitsPerPack;
+
+    std::random_device rd;
+    const unsigned seedBits = a.seed < 0 ? rd() : static_cast<unsigned>(a.seed);
+    const unsigned seedNoise = a.seed < 0 ? rd() : static_cast<unsigned>(a.seed + 1);
+    RandBitGen randGen(a.messageLen, seedBits);
+    PrbsBitGen prbsGen(a.messageLen, seedBits);
+    ConvolutionalEncoder convEnc(Dec::constLen, Dec::polyn1, Dec::polyn2);
+    AddNoise noise(static_cast<float>(std::pow(10.0, -a.snr / 5.0)), seedNoise);   // main.cpp:135
+    SoftDecisionPacker packer(Dec::inputType, 40000.0f);                            // main.cpp:137
+    ViterbiDecoder<options> viterbi;
+
+    ComputeElement& source = a.prbs ? static_cast<ComputeElement&>(prbsGen) : static_cast<ComputeElement&>(randGen);
+    Pipeline front = source.probe() | convEnc | noise | packer;
+    Pipeline pipe = front;
+    pipe.add(viterbi.probe());
+    PipelineResult result = pipe.run();
+    if (a.verbose) { std::cout << std::endl; pipe.printStatus(); std::cout << std::endl; }
+
+    Outcome out;
+    const decVec_t& decoded = std::any_cast<const decVec_t&>(result.final_output);
+    const Bits& gen = std::any_cast<const Bits&>(result.probed_outputs[0]);
+    out.decoded = decoded.size() * bitsPerPack;
+    for (size_t i = 0; i < out.decoded; ++i) {                                       // main.cpp:153-169
+        const bool d = (decoded[i / bitsPerPack] >> (bitsPerPack - 1 - i % bitsPerPack)) & 1u;
+        out.ben += d != (gen[i + Dec::extraL] == Bit::ON);
+    }
+    out.best_ms = std::any_cast<float>(viterbi.getStatus("GPU kernel time"));
+
+    // timed repeats / multi-GPU stream sharding on the packed channel words of this stream
+    if (a.reps > 1 || a.streams > 1 || a.gpus > 1) {
+        using encPack_t = typename Dec::encPack_t;
+        Pipeline regen = front;   // same seeds -> same stream
+        const auto packed = std::any_cast<std::vector<encPack_t>>(regen.run().final_output);
+        const size_t inputNum = packed.size() * Dec::encDataPerPack;
+        std::vector<double> gpu_ms(a.gpus, 0.0);
+        std::vector<double> best(a.gpus, 1e30);
+        std::vector<std::thread> workers;
+        for (int g = 0; g < a.gpus; ++g)
+            workers.emplace_back([&, g] {
+                Dec dec(inputNum, g);
+                decVec_t o(dec.getOutputSize(inputNum) / sizeof(typename Dec::decPack_t));
+                for (int s = g; s < a.streams; s += a.gpus) {        // stream s -> GPU s mod G
+                    double b = 1e30;
+                    for (int r = 0; r < a.reps; ++r) {
+                        float ms = 0.f;
+                        dec.run(const_cast<encPack_t*>(packed.data()), o.data(), inputNum, &ms);
+                        b = std::min<double>(b, ms);
+                    }
+                    gpu_ms[g] += b;
+                    best[g] = std::min(best[g], b);
+                }
+            });
+        for (auto& w : workers) w.join();
+        out.best_ms = *std::min_element(best.begin(), best.end());
+        const double box_ms = *std::max_element(gpu_ms.begin(), gpu_ms.end());
+        out.box_gbps = static_cast<double>(out.decoded) * a.streams / (box_ms * 1e6);
+    }
+    return out;
+}
+
+// runtime options -> template instantiation (the reference: 60 nested-macro cases, main.cpp:79-104)
+template <int options>
+bool tryRun(const Args& a, Outcome& out) {
+    if constexpr (OptionsValid<options>::value) {
+        if (a.options == options) { out = runPipeline<options>(a); return true; }
+    }
+    return false;
+}
+template <int... I>
+bool dispatch(const Args& a, Outcome& out, std::integer_sequence<int, I...>) {
+    // index = in + 5*(met + 3*(out + 2*cmp))
+    return (tryRun<((I % 5) << CHANNEL_SHIFT) | (((I / 5) % 3) << METRIC_SHIFT) | (((I / 15) % 2) << DECODE_SHIFT) |
+                   ((I / 30) << COMP_SHIFT)>(a, out) || ...);
+}
+
+int main(int argc, char* argv[]) {
+    const Args a = parseArg(argc, argv);
+    const int in = a.options & CHANNEL_MASK, met = a.options & METRIC_MASK;
+    if (met == M_B16 && in == SOFT16) {                                               // main.cpp:26-29
+        std::cerr << "Error: 16-bit metric does not support 16-bit soft decision input." << std::endl;
+        return -1;
+    }
+    if (a.verbose) {
+        static const char* inNames[] = {"Hard Decision", "4-bit Soft Decision", "8-bit Soft Decision", "16-bit Soft Decision", "32-bit Floating Point"};
+        std::cout << "Message Length: " << a.messageLen << "\nSNR: " << a.snr << " dB\n"
+                  << "Input Channel Type: " << inNames[in >> CHANNEL_SHIFT] << "\n"
+                  << "Metric Type: " << (met == M_B16 ? "16-bit" : met == M_B32 ? "32-bit" : "FP16") << "\n"
+                  << "Output Type: " << ((a.options & DECODE_MASK) == O_B16 ? "16-bit" : "32-bit") << "\n"
+                  << "Computation Mode: " << ((a.options & COMP_MASK) == REG ? "Regular" : "DPX") << "\n" << std::endl;
+    }
+    Outcome out;
+    if (!dispatch(a, out, std::make_integer_sequence<int, 60>{})) {
+        std::cerr << "Error: unsupported option combination." << std::endl;
+        return -1;
+    }
+    std::cout << "Pipeline executed." << std::endl;
+    std::cout << "Final results -> BEN: " << out.ben << "   BER: " << static_cast<double>(out.ben) / a.messageLen << std::endl;  // main.cpp:107-110
+    std::cout << "Decoder -> kernel time: " << out.best_ms << " ms   decoded: " << out.decoded << " bits   "
+              << out.decoded / (out.best_ms * 1e6) << " Gb/s";
+    if (out.box_gbps > 0) std::cout << "   box (" << a.streams << " streams / " << a.gpus << " GPUs): " << out.box_gbps << " Gb/s";
+    std::cout << std::endl;
+    return 0;
+}

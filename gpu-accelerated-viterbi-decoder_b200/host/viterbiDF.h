@@ -1,0 +1,180 @@
+// viterbiDF.h -- the reference's dataflow element library (reference src/viterbiDF.h:1-209) re-authored
+// over the C-ABI shim: RandBitGen | ConvolutionalEncoder | AddNoise | SoftDecisionPacker | ViterbiDecoder.
+// Same class names, constructor arguments, element value types and error behaviour
+// (std::runtime_error on a missing input, std::bad_any_cast on a wrong one).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <memory>
+#include <random>
+#include <sstream>
+#include <vector>
+
+#include "dataflow.h"
+#include "viterbi.h"
+
+enum class Bit : uint8_t { OFF = 0, ON = 1 };
+using Bits = std::vector<Bit>;
+using soft_t = int32_t;
+using Soft = std::vector<soft_t>;
+using Reals = std::vector<float>;
+
+namespace vit_detail {
+inline int parity(uint32_t v) { v ^= v >> 16; v ^= v >> 8; v ^= v >> 4; v ^= v >> 2; v ^= v >> 1; return v & 1; }
+}  // namespace vit_detail
+
+// 1) message source: mt19937 + uniform_int_distribution(0,1), as reference viterbiDF.h:20-33
+class RandBitGen : public ComputeElement {
+public:
+    explicit RandBitGen(size_t n, unsigned seed = 0) : n_(n), rng_(seed) {}
+    std::any process(const OptData&) override {
+        std::uniform_int_distribution<int> coin(0, 1);
+        Bits out(n_);
+        for (Bit& b : out) b = coin(rng_) ? Bit::ON : Bit::OFF;
+        return out;
+    }
+private:
+    size_t n_;
+    std::mt19937 rng_;
+};
+
+// 1b) PRBS-31 (x^31 + x^28 + 1) message source for reproducible bench inputs (new)
+class PrbsBitGen : public ComputeElement {
+public:
+    explicit PrbsBitGen(size_t n, uint32_t seed = 1) : n_(n), s_((0x7fffffffu ^ seed) & 0x7fffffffu) { if (!s_) s_ = 0x7fffffffu; }
+    std::any process(const OptData&) override {
+        Bits out(n_);
+        for (Bit& b : out) {
+            const uint32_t nb = ((s_ >> 30) ^ (s_ >> 27)) & 1u;
+            s_ = ((s_ << 1) | nb) & 0x7fffffffu;
+            b = nb ? Bit::ON : Bit::OFF;
+        }
+        return out;
+    }
+private:
+    size_t n_;
+    uint32_t s_;
+};
+
+// 2) rate-1/2 convolutional encoder: shift right, newest bit enters at bit CL-1 (viterbiDF.h:36-63)
+class ConvolutionalEncoder : public ComputeElement {
+public:
+    ConvolutionalEncoder(int CLength, uint32_t p0, uint32_t p1) : top_(CLength - 1), g0_(p0), g1_(p1) {}
+    std::any process(const OptData& in) override {
+        if (!in) throw std::runtime_error("ConvolutionalEncoder expects input bits");
+        const Bits& bits = std::any_cast<const Bits&>(*in);
+        Bits coded(2 * bits.size());
+        uint32_t sr = 0;
+        for (size_t i = 0; i < bits.size(); ++i) {
+            sr = (sr >> 1) | (static_cast<uint32_t>(bits[i] == Bit::ON) << top_);
+            coded[2 * i] = vit_detail::parity(sr & g0_) ? Bit::ON : Bit::OFF;
+            coded[2 * i + 1] = vit_detail::parity(sr & g1_) ? Bit::ON : Bit::OFF;
+        }
+        return coded;
+    }
+private:
+    int top_;
+    uint32_t g0_, g1_;
+};
+
+// 3) BPSK (+1 / -1) plus white Gaussian noise; stddev == infinity means "no noise" (viterbiDF.h:66-95)
+class AddNoise : public ComputeElement {
+public:
+    explicit AddNoise(float stddev = std::numeric_limits<float>::infinity(), unsigned seed = 0) : sd_(stddev), seed_(seed) {}
+    std::any process(const OptData& in) override {
+        if (!in) throw std::runtime_error("AddNoise expects input bits");
+        const Bits& bits = std::any_cast<const Bits&>(*in);
+        Reals out(bits.size());
+        const bool noiseless = sd_ == std::numeric_limits<float>::infinity();
+        std::mt19937 rng(seed_);
+        std::normal_distribution<float> gauss(0.0f, noiseless ? 1.0f : sd_);
+        for (size_t i = 0; i < bits.size(); ++i) {
+            const float s = bits[i] == Bit::ON ? 1.0f : -1.0f;
+            out[i] = noiseless ? s : s + gauss(rng);
+        }
+        return out;
+    }
+private:
+    float sd_;
+    unsigned seed_;
+};
+
+// 4) quantise and pack MSB-first into int32 words; FP32 passes (scaled) floats through (viterbiDF.h:98-167)
+class SoftDecisionPacker : public ComputeElement {
+public:
+    explicit SoftDecisionPacker(ChannelIn cfg, float scale = 1.0f) : cfg_(cfg), scale_(scale) {}
+    static soft_t quantise(ChannelIn cfg, float v) {
+        if (cfg == ChannelIn::HARD) return v > 0.0f ? 1 : 0;
+        const int width = cfg == ChannelIn::SOFT4 ? 4 : cfg == ChannelIn::SOFT8 ? 8 : 16;
+        long q = std::lrintf(v);
+        const long lo = -(1L << (width - 1)), hi = (1L << (width - 1)) - 1;
+        q = q < lo ? lo : q > hi ? hi : q;
+        return static_cast<soft_t>(q & ((1L << width) - 1));
+    }
+    std::any process(const OptData& in) override {
+        if (!in) throw std::runtime_error("SoftDecisionPacker expects input reals");
+        const Reals& src = std::any_cast<const Reals&>(*in);
+        if (cfg_ == ChannelIn::FP32) {
+            Reals out(src);
+            if (scale_ != 1.0f) for (float& v : out) v *= scale_;
+            return out;
+        }
+        const int width = cfg_ == ChannelIn::HARD ? 1 : cfg_ == ChannelIn::SOFT4 ? 4 : cfg_ == ChannelIn::SOFT8 ? 8 : 16;
+        const size_t per = 32 / width;
+        Soft out;
+        out.reserve(src.size() / per);
+        for (size_t i = 0; i + per <= src.size(); i += per) {
+            uint32_t w = 0;
+            for (size_t j = 0; j < per; ++j)
+                w = (width == 32 ? 0u : (w << width)) | static_cast<uint32_t>(quantise(cfg_, src[i + j] * scale_));
+            out.push_back(static_cast<soft_t>(w));
+        }
+        return out;
+    }
+private:
+    ChannelIn cfg_;
+    float scale_;
+};
+
+// 5) the decoder element: the caller of the drop-in boundary (viterbiDF.h:170-209)
+template <int options>
+struct ViterbiDecoder : ComputeElement {
+    using decPack_t = typename ViterbiCUDA<options>::decPack_t;
+    using decVec_t = std::vector<decPack_t>;
+    using encPack_t = typename ViterbiCUDA<options>::encPack_t;
+    static constexpr int bitsPerPack = ViterbiCUDA<options>::bitsPerPack;
+    static constexpr int encDataPerPack = ViterbiCUDA<options>::encDataPerPack;
+
+    ViterbiDecoder() : viterbi(new ViterbiCUDA<options>()) {}
+    explicit ViterbiDecoder(int messageLen) : viterbi(new ViterbiCUDA<options>(static_cast<size_t>(messageLen))) {}
+
+    std::any process(const OptData& in) override {
+        if (!in) throw std::runtime_error("ViterbiDecoder expects input reals");
+        const auto& soft = std::any_cast<const std::vector<encPack_t>&>(*in);
+        const size_t inputNum = soft.size() * encDataPerPack;
+        decVec_t out(viterbi->getOutputSize(inputNum) / sizeof(decPack_t));
+        float ms = 0.f;
+        viterbi->run(const_cast<encPack_t*>(soft.data()), out.data(), inputNum, &ms);
+        setStatus("GPU kernel time", ms);
+        setStatus("Decoded Gb/s", static_cast<float>(viterbi->getMessageLen(inputNum) / (ms * 1e6)));
+        return out;
+    }
+    std::string getStatusString(const std::string& key) const override {
+        std::ostringstream os;
+        os << std::fixed << std::setprecision(3);
+        if (key == "GPU kernel time") {
+            const float v = std::any_cast<float>(getStatus(key));
+            if (v < 1.0f) os << v * 1000.0f << " us";
+            else if (v < 1000.0f) os << v << " ms";
+            else os << v / 1000.0f << " s";
+            return os.str();
+        }
+        if (key == "Decoded Gb/s") { os << std::any_cast<float>(getStatus(key)); return os.str(); }
+        return ComputeElement::getStatusString(key);
+    }
+
+private:
+    std::unique_ptr<ViterbiCUDA<options>> viterbi;
+};
