@@ -71,9 +71,13 @@ struct vit_handle {
     int device = 0;
     unsigned segments = 6400;                 // reference viterbi.cu:19
     const vitk::KernelEntry* kernel = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in[2] = {nullptr, nullptr};
+    static constexpr int MAX_CHUNKS = 8;
+    cudaStream_t stream = nullptr;        // decode kernels
+    cudaStream_t chunk_stream[MAX_CHUNKS] = {};   // one per pipeline chunk so that chunk kernels co-reside
+    cudaStream_t copy_stream = nullptr;   // host -> device
+    cudaStream_t out_stream = nullptr;    // device -> host
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k0[MAX_CHUNKS] = {}, ev_k1[MAX_CHUNKS] = {};
     void* in_d = nullptr;  size_t in_cap = 0;
     void* out_d = nullptr; size_t out_cap = 0;
     void* pin_in = nullptr; size_t pin_in_cap = 0;
@@ -101,6 +105,29 @@ int ensure_device_buffers(vit_handle* h, size_t in_bytes, size_t out_bytes) {
     return VIT_OK;
 }
 
+// decode segments [seg_first, seg_limit) of every stream; timing (optional) between caller-supplied events
+int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t nstreams,
+                 size_t in_stride, size_t out_stride, cudaStream_t st, unsigned seg_first, unsigned seg_limit,
+                 cudaEvent_t e0, cudaEvent_t e1) {
+    const int o = h->options;
+    vitk::KParams kp;
+    kp.in = static_cast<const uint8_t*>(in_d);
+    kp.out = static_cast<uint8_t*>(out_d);
+    kp.in_stride = in_stride; kp.out_stride = out_stride;
+    kp.in_bytes = vit_input_size(o, inputNum);
+    kp.packs = vit_message_len(o, inputNum) / (size_t)bpp_of(o);
+    kp.segments = h->segments;
+    kp.seg_first = seg_first; kp.seg_limit = seg_limit;
+    kp.nstreams = (unsigned)nstreams;
+    kp.one = 1u;
+    dim3 grid((seg_limit - seg_first + vitk::SEGS_PER_WARP - 1) / vitk::SEGS_PER_WARP, (unsigned)nstreams, 1);
+    if (e0) VIT_CUDA(cudaEventRecord(e0, st));
+    VIT_CUDA(h->kernel->launch(kp, grid, st));
+    h->launches++;
+    if (e1) VIT_CUDA(cudaEventRecord(e1, st));
+    return VIT_OK;
+}
+
 int launch(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t nstreams,
            size_t in_stride, size_t out_stride, cudaStream_t st, float* kernel_ms) {
     const int o = h->options;
@@ -109,20 +136,10 @@ int launch(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t
     if ((reinterpret_cast<uintptr_t>(in_d) & 15) || (in_stride & 15))
         return fail(VIT_ERR_ARG, "device input must be 16-byte aligned (ptr %p, stride %zu)", in_d, in_stride);
     if (nstreams > 65535) return fail(VIT_ERR_ARG, "at most 65535 streams per launch (got %zu)", nstreams);
-    vitk::KParams kp;
-    kp.in = static_cast<const uint8_t*>(in_d);
-    kp.out = static_cast<uint8_t*>(out_d);
-    kp.in_stride = in_stride; kp.out_stride = out_stride;
-    kp.in_bytes = vit_input_size(o, inputNum);
-    kp.packs = M / (size_t)bpp_of(o);
-    kp.segments = h->segments;
-    kp.nstreams = (unsigned)nstreams;
-    dim3 grid((h->segments + vitk::SEGS_PER_WARP - 1) / vitk::SEGS_PER_WARP, (unsigned)nstreams, 1);
-    if (kernel_ms) VIT_CUDA(cudaEventRecord(h->ev0, st));
-    VIT_CUDA(h->kernel->launch(kp, grid, st));
-    h->launches++;
+    int rc = launch_range(h, in_d, out_d, inputNum, nstreams, in_stride, out_stride, st, 0, h->segments,
+                          kernel_ms ? h->ev0 : nullptr, kernel_ms ? h->ev1 : nullptr);
+    if (rc) return rc;
     if (kernel_ms) {
-        VIT_CUDA(cudaEventRecord(h->ev1, st));
         VIT_CUDA(cudaEventSynchronize(h->ev1));
         VIT_CUDA(cudaEventElapsedTime(kernel_ms, h->ev0, h->ev1));
     }
@@ -194,10 +211,15 @@ int vit_create(vit_handle** out, int options, int device, size_t prealloc_inputN
     h->options = options; h->device = device; h->kernel = entry_for(options);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in[0], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in[1], cudaEventDisableTiming);
+    for (int i = 0; i < vit_handle::MAX_CHUNKS && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&h->chunk_stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev_k0[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev_k1[i]);
+    }
     if (e != cudaSuccess) {
         vit_destroy(h);
         return fail(VIT_ERR_CUDA, "%s in %s at line %d", cudaGetErrorString(e), __FILE__, __LINE__);
@@ -219,9 +241,15 @@ void vit_destroy(vit_handle* h) {
     if (h->pin_out) cudaFreeHost(h->pin_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    for (int i = 0; i < 2; i++) if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    for (int i = 0; i < vit_handle::MAX_CHUNKS; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_k0[i]) cudaEventDestroy(h->ev_k0[i]);
+        if (h->ev_k1[i]) cudaEventDestroy(h->ev_k1[i]);
+        if (h->chunk_stream[i]) cudaStreamDestroy(h->chunk_stream[i]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
     delete h;
 }
 
@@ -252,12 +280,53 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
     if (out_bytes == 0) { if (kernel_ms) *kernel_ms = 0.f; return VIT_OK; }
     int rc = ensure_device_buffers(h, in_bytes, out_bytes);
     if (rc) return rc;
-    // host -> device (reference viterbi.cu:219), decode (viterbi.cu:228), device -> host (viterbi.cu:235)
-    VIT_CUDA(cudaMemcpyAsync(h->in_d, in_h, in_bytes, cudaMemcpyHostToDevice, h->stream));
-    rc = launch(h, h->in_d, h->out_d, inputNum, 1, 0, 0, h->stream, kernel_ms);
-    if (rc) return rc;
-    VIT_CUDA(cudaMemcpyAsync(out_h, h->out_d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
-    VIT_CUDA(cudaStreamSynchronize(h->stream));
+    const int o = h->options;
+    const size_t bpp = (size_t)bpp_of(o), W = h->segments;
+    int nch = (int)std::min<size_t>(vit_handle::MAX_CHUNKS, in_bytes / (4u << 20));
+    if (kernel_ms || nch < 2 || W < 64) {
+        // host -> device (reference viterbi.cu:219), decode (viterbi.cu:228), device -> host (viterbi.cu:235);
+        // kernel_ms = device time of the single decode launch, exactly the reference's measurement (viterbi.cu:224-232)
+        VIT_CUDA(cudaMemcpyAsync(h->in_d, in_h, in_bytes, cudaMemcpyHostToDevice, h->stream));
+        rc = launch(h, h->in_d, h->out_d, inputNum, 1, 0, 0, h->stream, kernel_ms);
+        if (rc) return rc;
+        VIT_CUDA(cudaMemcpyAsync(out_h, h->out_d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        VIT_CUDA(cudaStreamSynchronize(h->stream));
+        return VIT_OK;
+    }
+    // No timing requested: overlap the three phases.  The stream is cut at segment boundaries into nch
+    // chunks (segments are independent: chunk i needs the input bytes up to the end of its last segment's
+    // tail and produces a contiguous range of output packs).  Copies queue in order on one stream; each
+    // chunk's kernel runs on its own stream as soon as its bytes have landed, so the kernels co-reside
+    // (all 1600 warps fit on the device at once) instead of serialising.
+    const size_t P = vit_message_len(o, inputNum) / bpp, q = P / W, r = P % W;
+    const size_t b96 = in_type(o) == 0 ? 24 : in_type(o) == 1 ? 96 : in_type(o) == 2 ? 192 : in_type(o) == 3 ? 384 : 768;
+    auto start_pack = [&](size_t w) { return q * w + std::min(w, r); };
+    size_t in_lo = 0;
+    for (int i = 0; i < nch; i++) {
+        const unsigned a = (unsigned)(W * i / nch / 4 * 4), b = (i + 1 == nch) ? (unsigned)W : (unsigned)(W * (i + 1) / nch / 4 * 4);
+        size_t in_hi = in_bytes;
+        if (i + 1 < nch) {
+            const size_t last_bits = (q + ((size_t)(b - 1) < r ? 1 : 0)) * bpp;
+            const size_t end_stage = start_pack(b - 1) * bpp + 64 + 32 * ((last_bits + 31) / 32) + 32;
+            in_hi = std::min(in_bytes, (end_stage * b96 + 95) / 96 + 64);
+            in_hi = std::max(in_hi, in_lo);
+        }
+        if (in_hi > in_lo)
+            VIT_CUDA(cudaMemcpyAsync(static_cast<char*>(h->in_d) + in_lo, static_cast<const char*>(in_h) + in_lo,
+                                     in_hi - in_lo, cudaMemcpyHostToDevice, h->copy_stream));
+        in_lo = in_hi;
+        VIT_CUDA(cudaEventRecord(h->ev_in[i], h->copy_stream));
+        VIT_CUDA(cudaStreamWaitEvent(h->chunk_stream[i], h->ev_in[i], 0));
+        rc = launch_range(h, h->in_d, h->out_d, inputNum, 1, 0, 0, h->chunk_stream[i], a, b, nullptr, h->ev_k1[i]);
+        if (rc) return rc;
+        const size_t out_lo = start_pack(a) * bpp / 8, out_hi = (b >= W) ? out_bytes : start_pack(b) * bpp / 8;
+        VIT_CUDA(cudaStreamWaitEvent(h->out_stream, h->ev_k1[i], 0));
+        if (out_hi > out_lo)
+            VIT_CUDA(cudaMemcpyAsync(static_cast<char*>(out_h) + out_lo, static_cast<const char*>(h->out_d) + out_lo,
+                                     out_hi - out_lo, cudaMemcpyDeviceToHost, h->out_stream));
+    }
+    VIT_CUDA(cudaStreamSynchronize(h->out_stream));
+    for (int i = 0; i < nch; i++) VIT_CUDA(cudaStreamSynchronize(h->chunk_stream[i]));
     return VIT_OK;
 }
 

@@ -11,12 +11,14 @@
 //     with phase = stage % 6.  q bits 0,2,4 are lane bits, q bits 1,3,5 are register/half bits, so
 //     only phases 1,3,5 need warp shuffles; phases 2,4 are register-local and phase 0 is a
 //     half-swap (packed cores) or register-local (int32 core).
-//   * Everything is unrolled over the 96-stage period lcm(6 phases, 32-stage slide): all index
-//     math, shuffle masks, branch-metric operand choices and survivor-bit positions are immediates.
-//   * Branch metrics: the channel words arrive by 16-byte cp.async into a double-buffered raw
-//     staging area, are unpacked once per 48 stages into a shared-memory table of ready-to-add
-//     packed operands (one 8-byte entry per stage x lane-class), and each ACS stage costs one
-//     LDS.64 per lane.
+//   * A 96-stage super-step (lcm of the 6 phases and the 32-stage slide) is three straight-line
+//     slides, each a 5-iteration loop over the 6-stage phase period plus a 2-stage tail with the
+//     ring flush/traceback: shuffle masks, operand choices and row offsets are immediates, there is
+//     one loop branch per 6 stages, and the code (~15 KB) stays in the instruction cache.
+//   * Branch metrics: the channel words of the NEXT 96-stage super-step arrive by 16-byte cp.async
+//     into a raw staging area while the current super-step computes; once per super-step they are
+//     unpacked into a shared-memory table of ready-to-add packed operands (one 8-byte entry per
+//     stage x lane-class), so each ACS stage costs one LDS.64 per lane.
 //   * Survivors: 32-bit register-exchange words moved with predicated selects (VIMNMX.S16x2 yields
 //     both decision predicates).  The decision bits themselves are never shifted in one by one:
 //     the last 6 message bits of a survivor are its state index, so they are OR-ed in as a 6-bit
@@ -54,7 +56,10 @@ struct KParams {
     unsigned long long in_bytes;    // valid channel bytes per stream (reads beyond are zero-filled)
     unsigned long long packs;       // decoded packs per stream (messageLen / bitsPerPack)
     unsigned segments;              // stream segments (reference: 6400, viterbi.cu:19)
+    unsigned seg_first, seg_limit;  // this launch decodes segments [seg_first, seg_limit) (chunked host pipeline)
     unsigned nstreams;
+    unsigned one;                   // == 1, opaque to the compiler: `x*one + y` is emitted as IMAD so that
+                                    // the metric adds run on the FMA pipe while VIMNMX/SEL own the ALU pipe
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -63,7 +68,6 @@ struct KParams {
 constexpr int mod6(int x) { return ((x % 6) + 6) % 6; }
 constexpr int LANES_PER_SEG = 8;
 constexpr int SEGS_PER_WARP = 4;
-constexpr int CHUNK = 48;       // stages per branch-metric table build
 constexpr int SUPER = 96;       // unroll period
 
 // symbol bit 0 (poly 0171) depends on q bits {p+4,p+3,p+2}, symbol bit 1 (poly 0133) on {p+3,p+2,p}
@@ -123,11 +127,22 @@ template <int IN> constexpr int raw_pieces() { return (InTraits<IN>::B96 + 12 + 
 template <int IN> constexpr int b16_offset() { return IN == IN_HARD ? 1 : IN == IN_S8 ? 256 : 16; }
 
 // shared memory carve-up (per warp; one warp per block)
+// Operand table: row (stage) = 4 segments x 4 lane classes x 8 B = 128 B; rows are grouped by
+// j = stage/6 and each j-block is padded by 16 B so that the 8 lanes of a group, which build rows
+// 6 apart, store to 8 different 16-byte bank columns (conflict-free STS.128).
+constexpr int BM_ROW = SEGS_PER_WARP * 4 * 8;            // 128
+constexpr int BM_JBLOCK = 6 * BM_ROW + 16;               // 784
+constexpr int row_off(int s) { return (s / 6) * BM_JBLOCK + (s % 6) * BM_ROW; }   // stage within super-step -> table row
+// Ring: per (slot, segment) 64 words + 16 B pad; lane l stores its 8 words at l*32 + (l>>2)*16 so that
+// the two STS.128 of a flush are conflict-free as well.
+constexpr int RING_SEG = 64 * 4 + 16;                    // 272
+constexpr int ring_word_of(int l, int r) { return l * 8 + (l >> 2) * 4 + r; }
+
 template <int IN> struct Smem {
-    static constexpr int BM_BYTES = CHUNK * SEGS_PER_WARP * 4 * 8;                 // 6144
+    static constexpr int BM_BYTES = (SUPER / 6) * BM_JBLOCK;                       // 12544
     static constexpr int RAW_SEG = raw_pieces<IN>() * 16;
-    static constexpr int RAW_BYTES = 2 * SEGS_PER_WARP * RAW_SEG;
-    static constexpr int RING_BYTES = 3 * SEGS_PER_WARP * 64 * 4;                  // 3072
+    static constexpr int RAW_BYTES = SEGS_PER_WARP * RAW_SEG;      // single buffer: consumed whole by the table build
+    static constexpr int RING_BYTES = 3 * SEGS_PER_WARP * RING_SEG;                // 3264
     static constexpr int LUT_BYTES = 3 * 64;
     static constexpr int OFF_BM = 0;
     static constexpr int OFF_RAW = OFF_BM + BM_BYTES;
@@ -203,8 +218,10 @@ template <int MET, int IN> struct Core;
 template <int IN> struct Core<MET_B16, IN> {
     static constexpr bool PACKED = true;
     static constexpr uint32_t K2 = (uint32_t)(2 * b16_offset<IN>()) * 0x10001u;
-    static VIT_HD uint32_t plus(uint32_t pm, uint32_t w) { return pm + w; }
-    static VIT_HD uint32_t minus(uint32_t pm, uint32_t w) { return pm - w + K2; }
+    // all metric adds are `x*one + y` = IMAD on the FMA pipe; the ALU pipe is left to VIMNMX/SEL
+    static VIT_HD uint32_t plus(uint32_t pm, uint32_t w, uint32_t one) { return pm * one + w; }
+    // operand of the opposite branch: (c - b) per half = K2 - w, no borrow because w <= K2 per half
+    static VIT_HD uint32_t neg(uint32_t w, uint32_t one) { return w * (0u - one) + K2; }
     // returns max(partner, own); p* = partner chosen; partner wins ties (reference int16 core,
     // viterbiACS.cuh:112-119,215-220: __vibmax_s16x2(partner - bm, own + bm) -> pred = (a >= b))
     static VIT_HD uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool /*own_wins_tie*/) {
@@ -236,8 +253,8 @@ template <int IN> struct Core<MET_F16, IN> {
 #if defined(__CUDA_ARCH__)
     static VIT_D __half2 h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
     static VIT_D uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-    static VIT_D uint32_t plus(uint32_t pm, uint32_t w) { return u32(__hadd2(h2(pm), h2(w))); }
-    static VIT_D uint32_t minus(uint32_t pm, uint32_t w) { return u32(__hsub2(h2(pm), h2(w))); }
+    static VIT_D uint32_t plus(uint32_t pm, uint32_t w, uint32_t) { return u32(__hadd2(h2(pm), h2(w))); }
+    static VIT_D uint32_t neg(uint32_t w, uint32_t) { return u32(__hneg2(h2(w))); }   // folds into HADD2's -operand
     // own wins ties (reference half2 core, viterbiACS.cuh:146-157,249-256: __hlt2_mask(own, partner))
     static VIT_D uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool) {
         __half2 a = h2(part), b = h2(own);
@@ -249,15 +266,15 @@ template <int IN> struct Core<MET_F16, IN> {
     static VIT_D uint32_t sub(uint32_t a, uint32_t m) { return u32(__hsub2(h2(a), h2(m))); }
     static VIT_D uint32_t enc(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v)); }
 #else
-    static uint32_t plus(uint32_t pm, uint32_t w) { EmuH2 a = emu_h2_unpack(pm), b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{a.lo + b.lo, a.hi + b.hi}); }
-    static uint32_t minus(uint32_t pm, uint32_t w) { EmuH2 a = emu_h2_unpack(pm), b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{a.lo - b.lo, a.hi - b.hi}); }
+    static uint32_t plus(uint32_t pm, uint32_t w, uint32_t) { EmuH2 a = emu_h2_unpack(pm), b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{a.lo + b.lo, a.hi + b.hi}); }
+    static uint32_t neg(uint32_t w, uint32_t) { EmuH2 b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{-b.lo, -b.hi}); }
     static uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool) {
         EmuH2 a = emu_h2_unpack(part), b = emu_h2_unpack(own);
         p_lo = a.lo > b.lo; p_hi = a.hi > b.hi;
         return emu_h2_pack(EmuH2{p_lo ? a.lo : b.lo, p_hi ? a.hi : b.hi});
     }
     static uint32_t vmin(uint32_t a, uint32_t b) { EmuH2 x = emu_h2_unpack(a), y = emu_h2_unpack(b); return emu_h2_pack(EmuH2{x.lo < y.lo ? x.lo : y.lo, x.hi < y.hi ? x.hi : y.hi}); }
-    static uint32_t sub(uint32_t a, uint32_t m) { return minus(a, m); }
+    static uint32_t sub(uint32_t a, uint32_t m) { return plus(a, neg(m, 1), 1); }
     static uint32_t enc(int v) { return (uint32_t)(uint16_t)(int16_t)v; }
 #endif
     static VIT_HD uint32_t zero() { return 0; }
@@ -266,8 +283,8 @@ template <int IN> struct Core<MET_F16, IN> {
 // ---- int32: one state per register --------------------------------------------------------------
 template <int IN> struct Core<MET_B32, IN> {
     static constexpr bool PACKED = false;
-    static VIT_HD uint32_t plus(uint32_t pm, uint32_t w) { return pm + w; }
-    static VIT_HD uint32_t minus(uint32_t pm, uint32_t w) { return pm - w; }
+    static VIT_HD uint32_t plus(uint32_t pm, uint32_t w, uint32_t one) { return pm * one + w; }      // IMAD
+    static VIT_HD uint32_t neg(uint32_t w, uint32_t one) { return w * (0u - one); }
     // partner wins ties except where the reference's phase-0 rule makes the odd predecessor win
     // (viterbiACS.cuh:136-142: both selfPM compares are "odd-candidate >= even-candidate")
     static VIT_HD uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool own_wins_tie) {
@@ -293,16 +310,19 @@ template <int MET> struct LaneState {
 
 // candidate of `metric` along the branch whose operand type is `type` (see bm_type), given the
 // table entry (w0 = X word, w1 = Y word); `opposite` = the other branch into the same state
+struct Operands { uint32_t x, y, nx, ny, one; };   // +X, +Y, -X, -Y in the core's operand encoding
+
+
 template <class C, int TYPE, bool OPPOSITE>
-VIT_HD uint32_t cand(uint32_t metric, uint32_t w0, uint32_t w1) {
+VIT_HD uint32_t cand(uint32_t metric, const Operands& o) {
     constexpr bool useY = (TYPE == 1 || TYPE == 2);
     constexpr bool neg = ((TYPE == 2 || TYPE == 3) != OPPOSITE);
-    return neg ? C::minus(metric, useY ? w1 : w0) : C::plus(metric, useY ? w1 : w0);
+    return C::plus(metric, neg ? (useY ? o.ny : o.nx) : (useY ? o.y : o.x), o.one);
 }
 
 // one trellis stage at phase P (static).  lane bits are the low 3 bits of the lane id.
 template <int MET, int IN, int P>
-VIT_HD void acs_stage(LaneState<MET>& s, uint32_t w0, uint32_t w1) {
+VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
     using C = Core<MET, IN>;
     constexpr int KIND = stage_kind<MET>(P);
     constexpr int BIT = stage_bit(P);
@@ -317,8 +337,8 @@ VIT_HD void acs_stage(LaneState<MET>& s, uint32_t w0, uint32_t w1) {
 #define VIT_LANE_PACKED(r)                                                                        \
     {                                                                                             \
         bool pl, ph;                                                                              \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], w0, w1);                             \
-        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], w0, w1);                               \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                             \
+        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                               \
         s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
         s.pp[r] = pl ? ppp[r] : s.pp[r];                                                          \
         s.pp[r + 4] = ph ? ppp[r + 4] : s.pp[r + 4];                                              \
@@ -329,8 +349,8 @@ VIT_HD void acs_stage(LaneState<MET>& s, uint32_t w0, uint32_t w1) {
 #define VIT_LANE_B32(r)                                                                           \
     {                                                                                             \
         bool pl, ph;                                                                              \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], w0, w1);                             \
-        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], w0, w1);                               \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                             \
+        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                               \
         s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
         s.pp[r] = pl ? ppp[r] : s.pp[r];                                                          \
     }
@@ -344,8 +364,8 @@ VIT_HD void acs_stage(LaneState<MET>& s, uint32_t w0, uint32_t w1) {
     {                                                                                             \
         bool pl, ph;                                                                              \
         uint32_t sw = prmt(s.pm[r], 0, 0x1032);                                                   \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], w0, w1);                             \
-        uint32_t pc = cand<C, bm_type(r, P), true>(sw, w0, w1);                                   \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                             \
+        uint32_t pc = cand<C, bm_type(r, P), true>(sw, ops);                                   \
         s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
         uint32_t a = s.pp[r], b = s.pp[r + 4];                                                    \
         s.pp[r] = pl ? b : a;                                                                     \
@@ -361,10 +381,10 @@ VIT_HD void acs_stage(LaneState<MET>& s, uint32_t w0, uint32_t w1) {
         constexpr int rb = ra | (1 << BIT);                                                       \
         bool al, ah, bl, bh;                                                                      \
         uint32_t ea = s.pm[ra], eb = s.pm[rb];                                                    \
-        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, w0, w1),                        \
-                                cand<C, bm_type(ra, P), false>(ea, w0, w1), al, ah, false);       \
-        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, w0, w1),                        \
-                                cand<C, bm_type(rb, P), false>(eb, w0, w1), bl, bh, false);       \
+        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, ops),                        \
+                                cand<C, bm_type(ra, P), false>(ea, ops), al, ah, false);       \
+        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, ops),                        \
+                                cand<C, bm_type(rb, P), false>(eb, ops), bl, bh, false);       \
         s.pm[ra] = na; s.pm[rb] = nb;                                                             \
         uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb], pa1 = s.pp[ra + 4], pb1 = s.pp[rb + 4];          \
         s.pp[ra] = al ? pb0 : pa0; s.pp[rb] = bl ? pa0 : pb0;                                     \
@@ -381,10 +401,10 @@ VIT_HD void acs_stage(LaneState<MET>& s, uint32_t w0, uint32_t w1) {
         constexpr int rb = ra | (1 << BIT);                                                       \
         bool al, ah, bl, bh;                                                                      \
         uint32_t ea = s.pm[ra], eb = s.pm[rb];                                                    \
-        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, w0, w1),                        \
-                                cand<C, bm_type(ra, P), false>(ea, w0, w1), al, ah, false);       \
-        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, w0, w1),                        \
-                                cand<C, bm_type(rb, P), false>(eb, w0, w1), bl, bh, ODD_WINS);    \
+        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, ops),                        \
+                                cand<C, bm_type(ra, P), false>(ea, ops), al, ah, false);       \
+        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, ops),                        \
+                                cand<C, bm_type(rb, P), false>(eb, ops), bl, bh, ODD_WINS);    \
         s.pm[ra] = na; s.pm[rb] = nb;                                                             \
         uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb];                                                  \
         s.pp[ra] = al ? pb0 : pa0; s.pp[rb] = bl ? pa0 : pb0;                                     \
@@ -511,7 +531,9 @@ struct WarpCtx {
     LaneState<MET> st;
     uint8_t* smem;
     int lane, g, l;
+    uint32_t one;
     uint32_t bm_off[6];        // byte offset of this lane's class entry within a stage row, per phase
+    uint32_t bm_offn[6];       // ... and of the complementary class (3 - class): the same operands negated
     uint32_t lane_field[3];    // phases 1,3,5
     // segment geometry
     unsigned long long seg_byte0;   // byte offset of the segment's first stage in the stream
@@ -524,12 +546,12 @@ struct WarpCtx {
 };
 
 template <int MET, int IN, int BPP>
-VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP>& c, unsigned super_idx, int buf) {
+VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP>& c, unsigned super_idx) {
     using S = Smem<IN>;
     constexpr int B96 = InTraits<IN>::B96;
     unsigned long long b0 = c.seg_byte0 + (unsigned long long)super_idx * B96;
     unsigned long long al = b0 & ~15ull;
-    uint8_t* dst = c.smem + S::OFF_RAW + (buf * SEGS_PER_WARP + c.g) * S::RAW_SEG;
+    uint8_t* dst = c.smem + S::OFF_RAW + c.g * S::RAW_SEG;
 #pragma unroll
     for (int i = 0; i < (raw_pieces<IN>() + 7) / 8; i++) {
         int piece = c.l + 8 * i;
@@ -543,14 +565,15 @@ VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP>& c, unsigned super_idx, int buf
     cp_async_commit();
 }
 
+// lane l of the group builds the rows of stages P + 6*(l + 8*round): j-block l + 8*round, row P
 template <int MET, int IN, int BPP, int P>
-VIT_HD void build_phase(WarpCtx<MET, IN, BPP>& c, int half, int buf, unsigned skew) {
+VIT_HD void build_phase(WarpCtx<MET, IN, BPP>& c, int round, unsigned skew) {
     using S = Smem<IN>;
-    const uint8_t* raw = c.smem + S::OFF_RAW + (buf * SEGS_PER_WARP + c.g) * S::RAW_SEG + skew;
-    int srel = half * CHUNK + P + 6 * c.l;       // stage within superchunk
+    const uint8_t* raw = c.smem + S::OFF_RAW + c.g * S::RAW_SEG + skew;
+    const int j = c.l + 8 * round;
     uint32_t e[8];
-    build_step<MET, IN, P>(raw, srel, e);
-    uint32_t* row = reinterpret_cast<uint32_t*>(c.smem + S::OFF_BM + ((P + 6 * c.l) * SEGS_PER_WARP + c.g) * 32);
+    build_step<MET, IN, P>(raw, P + 6 * j, e);
+    uint32_t* row = reinterpret_cast<uint32_t*>(c.smem + S::OFF_BM + j * BM_JBLOCK + P * BM_ROW + c.g * 32);
 #if defined(__CUDA_ARCH__)
     reinterpret_cast<uint4*>(row)[0] = make_uint4(e[0], e[1], e[2], e[3]);
     reinterpret_cast<uint4*>(row)[1] = make_uint4(e[4], e[5], e[6], e[7]);
@@ -560,13 +583,16 @@ VIT_HD void build_phase(WarpCtx<MET, IN, BPP>& c, int half, int buf, unsigned sk
 }
 
 template <int MET, int IN, int BPP>
-VIT_HD void build_table(WarpCtx<MET, IN, BPP>& c, int half, int buf, unsigned skew) {
-    build_phase<MET, IN, BPP, 0>(c, half, buf, skew);
-    build_phase<MET, IN, BPP, 1>(c, half, buf, skew);
-    build_phase<MET, IN, BPP, 2>(c, half, buf, skew);
-    build_phase<MET, IN, BPP, 3>(c, half, buf, skew);
-    build_phase<MET, IN, BPP, 4>(c, half, buf, skew);
-    build_phase<MET, IN, BPP, 5>(c, half, buf, skew);
+VIT_HD void build_table(WarpCtx<MET, IN, BPP>& c, unsigned skew) {
+#pragma unroll 1
+    for (int round = 0; round < 2; round++) {
+        build_phase<MET, IN, BPP, 0>(c, round, skew);
+        build_phase<MET, IN, BPP, 1>(c, round, skew);
+        build_phase<MET, IN, BPP, 2>(c, round, skew);
+        build_phase<MET, IN, BPP, 3>(c, round, skew);
+        build_phase<MET, IN, BPP, 4>(c, round, skew);
+        build_phase<MET, IN, BPP, 5>(c, round, skew);
+    }
 }
 
 // subtract the segment-wide minimum metric (a common offset never changes a decision; the
@@ -590,16 +616,16 @@ template <int MET, int IN> constexpr int norm_period() {
     return (MET == MET_B16 && IN == IN_S8) ? 32 : (MET == MET_F16 && (IN == IN_S8 || IN == IN_S16)) ? 32 : 96;
 }
 
-// end of a 32-stage slide at superchunk stage S (S % 32 == 31): flush the register-exchange words
-// to ring slot S/32, trace back from state 0, emit one 32-bit word of decoded bits.
-template <int MET, int IN, int BPP, int S>
+// End of a 32-stage slide (superchunk stage S = 32*SLOT + 31, phase P = S % 6): flush the
+// register-exchange words to ring slot SLOT, trace back from state 0, emit 32 decoded bits, start
+// the next survivor word.
+template <int MET, int IN, int BPP, int SLOT>
 VIT_HD void slide_end(WarpCtx<MET, IN, BPP>& c) {
     using SM = Smem<IN>;
-    constexpr int SLOT = S / 32;
-    constexpr int P = S % 6;                      // phase of stage e (1, 3 or 5)
-    constexpr int LUTV = SLOT;                    // lut variant: word at e-32 has phase (P+4)%6
-    uint32_t* ring = reinterpret_cast<uint32_t*>(c.smem + SM::OFF_RING);
-    uint32_t* mine = ring + (SLOT * SEGS_PER_WARP + c.g) * 64 + c.l * 8;
+    constexpr int S = 32 * SLOT + 31;
+    constexpr int P = S % 6;                      // 1, 3, 5 for slots 0, 1, 2
+    uint8_t* ringb = c.smem + SM::OFF_RING;
+    uint32_t* mine = reinterpret_cast<uint32_t*>(ringb + (SLOT * SEGS_PER_WARP + c.g) * RING_SEG) + ring_word_of(c.l, 0);
 #if defined(__CUDA_ARCH__)
     reinterpret_cast<uint4*>(mine)[0] = make_uint4(c.st.pp[0], c.st.pp[1], c.st.pp[2], c.st.pp[3]);
     reinterpret_cast<uint4*>(mine)[1] = make_uint4(c.st.pp[4], c.st.pp[5], c.st.pp[6], c.st.pp[7]);
@@ -612,9 +638,10 @@ VIT_HD void slide_end(WarpCtx<MET, IN, BPP>& c) {
     const unsigned e = c.t0 + S;
     if (e >= 95) {
         unsigned st1 = brev32(w_e) & 63u;                                   // reference viterbiTB.cuh:9-12
-        const uint8_t* lut = c.smem + SM::OFF_LUT + LUTV * 64;
+        const uint8_t* lut = c.smem + SM::OFF_LUT + SLOT * 64;             // word at e-32 has phase (P+4)%6
         unsigned idx = lut[st1];
-        uint32_t word = ring[(((SLOT + 2) % 3) * SEGS_PER_WARP + c.g) * 64 + idx];   // viterbiTB.cuh:14-19
+        const uint32_t* prev = reinterpret_cast<const uint32_t*>(ringb + (((SLOT + 2) % 3) * SEGS_PER_WARP + c.g) * RING_SEG);
+        uint32_t word = prev[idx];                                          // viterbiTB.cuh:14-19
         unsigned k = (e - 95) / 32;                                         // slide index
         if (c.l == 0) {
             if constexpr (BPP == 32) {
@@ -628,39 +655,64 @@ VIT_HD void slide_end(WarpCtx<MET, IN, BPP>& c) {
     }
     // start the next word: message bits e-5..e are the state index
     insert_field<MET, P, 26, 6, true>(c.st, c.lane_field[P / 2]);
+    if constexpr (norm_period<MET, IN>() == 32) normalize<MET, IN>(c.st);
 }
 
-template <int MET, int IN, int BPP, int S>
-VIT_HD void one_stage(WarpCtx<MET, IN, BPP>& c) {
-    using SM = Smem<IN>;
-    constexpr int P = S % 6;
-    const uint32_t* ent = reinterpret_cast<const uint32_t*>(c.smem + SM::OFF_BM + (S % CHUNK) * (SEGS_PER_WARP * 32) + c.bm_off[P]);
-#if defined(__CUDA_ARCH__)
-    uint2 w = *reinterpret_cast<const uint2*>(ent);
-    acs_stage<MET, IN, P>(c.st, w.x, w.y);
-#else
-    acs_stage<MET, IN, P>(c.st, ent[0], ent[1]);
-#endif
-    constexpr int V = S % 32;
-    if constexpr (V == 31) slide_end<MET, IN, BPP, S>(c);
-    else if constexpr (V == 5) insert_field<MET, P, 20, 6, false>(c.st, c.lane_field[P / 2]);
-    else if constexpr (V == 11) insert_field<MET, P, 14, 6, false>(c.st, c.lane_field[P / 2]);
-    else if constexpr (V == 17) insert_field<MET, P, 8, 6, false>(c.st, c.lane_field[P / 2]);
-    else if constexpr (V == 23) insert_field<MET, P, 2, 6, false>(c.st, c.lane_field[P / 2]);
-    else if constexpr (V == 29) insert_field<MET, P, 0, 2, false>(c.st, c.lane_field[P / 2]);
-}
-
-template <int MET, int IN, int BPP, int S0, int S1>
-struct StageRange {
-    static VIT_HD void run(WarpCtx<MET, IN, BPP>& c) {
-        one_stage<MET, IN, BPP, S0>(c);
-        StageRange<MET, IN, BPP, S0 + 1, S1>::run(c);
+// i-th insertion batch of a survivor word (i = 0..4), all at phase P: 6 bits at 20,14,8,2, then 2 bits at 0
+template <int MET, int P>
+VIT_HD void insert_batch(LaneState<MET>& st, uint32_t lane_field, int i) {
+    switch (i) {
+        case 0: insert_field<MET, P, 20, 6, false>(st, lane_field); break;
+        case 1: insert_field<MET, P, 14, 6, false>(st, lane_field); break;
+        case 2: insert_field<MET, P, 8, 6, false>(st, lane_field); break;
+        case 3: insert_field<MET, P, 2, 6, false>(st, lane_field); break;
+        default: insert_field<MET, P, 0, 2, false>(st, lane_field); break;
     }
-};
-template <int MET, int IN, int BPP, int S1>
-struct StageRange<MET, IN, BPP, S1, S1> {
-    static VIT_HD void run(WarpCtx<MET, IN, BPP>&) {}
-};
+}
+
+// stage S of the super-step; tbl = table base advanced by the loop iteration (i * BM_JBLOCK)
+template <int MET, int IN, int BPP, int S>
+VIT_HD void one_stage(WarpCtx<MET, IN, BPP>& c, const uint8_t* tbl) {
+    constexpr int P = S % 6;
+    // class c holds (X, Y) in the core's operand encoding; class 3-c holds exactly (-X, -Y), so the
+    // operands of the opposite branches cost a second LDS.64 instead of arithmetic
+    const uint32_t* ent = reinterpret_cast<const uint32_t*>(tbl + row_off(S) + c.bm_off[P]);
+    const uint32_t* entn = reinterpret_cast<const uint32_t*>(tbl + row_off(S) + c.bm_offn[P]);
+#if defined(__CUDA_ARCH__)
+    const uint2 w = *reinterpret_cast<const uint2*>(ent);
+    const uint2 n = *reinterpret_cast<const uint2*>(entn);
+    acs_stage<MET, IN, P>(c.st, Operands{w.x, w.y, n.x, n.y, c.one});
+#else
+    acs_stage<MET, IN, P>(c.st, Operands{ent[0], ent[1], entn[0], entn[1], c.one});
+#endif
+}
+
+// One 32-stage slide = survivor word W of the super-step (stages 32W .. 32W+31):
+//   5 x { 6 stages ; insertion batch i }   (batches land on stages 32W+5, +11, +17, +23, +29)
+//   2 stages ; flush + traceback + emit     (stage 32W+31)
+// One loop branch and one batch dispatch per 6 stages; everything else is straight-line.
+// Returns true when the segment group has emitted its last word.
+template <int MET, int IN, int BPP, int W>
+VIT_HD bool slide(WarpCtx<MET, IN, BPP>& c, unsigned Tmax) {
+    using SM = Smem<IN>;
+    constexpr int S0 = 32 * W;
+    constexpr int PB = (S0 + 5) % 6;              // phase of the batch stages: 5, 1, 3
+    const uint8_t* tbl = c.smem + SM::OFF_BM;
+#pragma unroll 1
+    for (int i = 0; i < 5; i++, tbl += BM_JBLOCK) {
+        one_stage<MET, IN, BPP, S0 + 0>(c, tbl);
+        one_stage<MET, IN, BPP, S0 + 1>(c, tbl);
+        one_stage<MET, IN, BPP, S0 + 2>(c, tbl);
+        one_stage<MET, IN, BPP, S0 + 3>(c, tbl);
+        one_stage<MET, IN, BPP, S0 + 4>(c, tbl);
+        one_stage<MET, IN, BPP, S0 + 5>(c, tbl);
+        insert_batch<MET, PB>(c.st, c.lane_field[PB / 2], i);
+    }
+    one_stage<MET, IN, BPP, S0 + 30>(c, c.smem + SM::OFF_BM);
+    one_stage<MET, IN, BPP, S0 + 31>(c, c.smem + SM::OFF_BM);
+    slide_end<MET, IN, BPP, W>(c);
+    return c.t0 + 32 * (W + 1) >= Tmax;
+}
 
 // Decode the 4 segments owned by warp `warp_id` of stream `stream`.
 template <int MET, int IN, int BPP>
@@ -668,12 +720,13 @@ VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int 
     using SM = Smem<IN>;
     WarpCtx<MET, IN, BPP> c;
     c.smem = smem; c.lane = lane; c.g = lane >> 3; c.l = lane & 7;
+    c.one = kp.one;
 
     // segment partition, reference viterbi.cu:156-165
     const unsigned W = kp.segments;
     const unsigned long long q = kp.packs / W, rem = kp.packs % W;
-    const unsigned long long w = (unsigned long long)warp_id * SEGS_PER_WARP + c.g;
-    unsigned long long Lp = (w < W) ? q + (w < rem ? 1 : 0) : 0;
+    const unsigned long long w = (unsigned long long)kp.seg_first + (unsigned long long)warp_id * SEGS_PER_WARP + c.g;
+    unsigned long long Lp = (w < kp.seg_limit) ? q + (w < rem ? 1 : 0) : 0;
     const unsigned long long start_pack = q * w + (w < rem ? w : rem);
     c.seg_bits = (unsigned)(Lp * BPP);
     c.out_word0 = start_pack;
@@ -684,15 +737,18 @@ VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int 
     c.in_bytes = kp.in_bytes;
 
     // the first segment of the warp is never shorter than the others
-    const unsigned long long w_first = (unsigned long long)warp_id * SEGS_PER_WARP;
-    const unsigned long long Lp_first = (w_first < W) ? q + (w_first < rem ? 1 : 0) : 0;
+    const unsigned long long w_first = (unsigned long long)kp.seg_first + (unsigned long long)warp_id * SEGS_PER_WARP;
+    const unsigned long long Lp_first = (w_first < kp.seg_limit) ? q + (w_first < rem ? 1 : 0) : 0;
     if (Lp_first == 0) return;
     const unsigned Lmax = (unsigned)(Lp_first * BPP);
     const unsigned Tmax = 64 + 32 * ((Lmax + 31) / 32);                   // viterbi.cu:176-197
     const unsigned nsuper = (Tmax + SUPER - 1) / SUPER;
 
 #pragma unroll
-    for (int p = 0; p < 6; p++) c.bm_off[p] = (uint32_t)(c.g * 32 + lane_class_of(c.l, p) * 8);
+    for (int p = 0; p < 6; p++) {
+        c.bm_off[p] = (uint32_t)(c.g * 32 + lane_class_of(c.l, p) * 8);
+        c.bm_offn[p] = (uint32_t)(c.g * 32 + (3 - lane_class_of(c.l, p)) * 8);
+    }
 #pragma unroll
     for (int i = 0; i < 3; i++) c.lane_field[i] = lane_field_of(c.l, 2 * i + 1);
 #pragma unroll
@@ -700,39 +756,31 @@ VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int 
 #pragma unroll
     for (int k = 0; k < 8; k++) c.st.pp[k] = 0;
 
-    // traceback lookup: variant v (ring slot of e) -> position of a state at phase of stage e-32
+    // traceback lookup: variant v (ring slot of e) -> ring word of a state at the phase of stage e-32
     {
         uint8_t* lut = smem + SM::OFF_LUT;
         for (int i = lane; i < 3 * 64; i += 32) {
             int v = i / 64, st = i % 64;
             int pw = mod6((v * 32 + 31) + 4);                           // phase of stage e-32
-            lut[i] = (uint8_t)pos_index_of_state(st, pw);
+            int pos = pos_index_of_state(st, pw);                       // lane*8 + reg
+            lut[i] = (uint8_t)ring_word_of(pos >> 3, pos & 7);
         }
     }
 
-    issue_raw_copy(c, 0, 0);
+    issue_raw_copy(c, 0);
+#pragma unroll 1
     for (unsigned sc = 0; sc < nsuper; sc++) {
-        const int buf = (int)(sc & 1);
         c.t0 = sc * SUPER;
         const unsigned skew = (unsigned)((c.seg_byte0 + (unsigned long long)sc * InTraits<IN>::B96) & 15ull);
-        if (sc + 1 < nsuper) { issue_raw_copy(c, sc + 1, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        cp_async_wait<0>();
         syncwarp();
-
-        normalize<MET, IN>(c.st);
-        build_table(c, 0, buf, skew);
+        build_table(c, skew);
         syncwarp();
-        StageRange<MET, IN, BPP, 0, 32>::run(c);
-        if constexpr (norm_period<MET, IN>() == 32) normalize<MET, IN>(c.st);
-        if (c.t0 + 32 >= Tmax) break;
-        StageRange<MET, IN, BPP, 32, 48>::run(c);
-        syncwarp();
-        build_table(c, 1, buf, skew);
-        syncwarp();
-        StageRange<MET, IN, BPP, 48, 64>::run(c);
-        if constexpr (norm_period<MET, IN>() == 32) normalize<MET, IN>(c.st);
-        if (c.t0 + 64 >= Tmax) break;
-        StageRange<MET, IN, BPP, 64, 96>::run(c);
+        if (sc + 1 < nsuper) issue_raw_copy(c, sc + 1);       // lands while the 96 stages below run
+        if constexpr (norm_period<MET, IN>() != 32) normalize<MET, IN>(c.st);
+        if (slide<MET, IN, BPP, 0>(c, Tmax)) break;
+        if (slide<MET, IN, BPP, 1>(c, Tmax)) break;
+        if (slide<MET, IN, BPP, 2>(c, Tmax)) break;
         syncwarp();
     }
 }

@@ -109,7 +109,7 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     g_job.kp.in = (const uint8_t*)in; g_job.kp.out = (uint8_t*)out;
     g_job.kp.in_stride = in_stride; g_job.kp.out_stride = out_stride;
     g_job.kp.in_bytes = in_bytes; g_job.kp.packs = M / bpp;
-    g_job.kp.segments = segments; g_job.kp.nstreams = nstreams;
+    g_job.kp.segments = segments; g_job.kp.seg_first = 0; g_job.kp.seg_limit = segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u;
     g_job.met = mt == 0 ? vitk::MET_B32 : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
     g_job.in = it; g_job.bpp = bpp;
     g_job.smem = (uint8_t*)aligned_alloc(128, 64 * 1024);
