@@ -287,17 +287,31 @@ def main():
         if pad:
             packed = torch.cat([packed, torch.zeros(pad, dtype=torch.uint8, device=dev)])
         streams.append((bits if k == 0 else None, packed))
-    d_out = torch.zeros((out_bytes + 255) // 256 * 256, dtype=torch.uint8, device=dev)
-    gathered = [torch.empty_like(d_out) for _ in range(world)] if world > 1 else None
+    # two output buffers: the NCCL gather of step k overlaps the decode of step k+1
+    d_outs = [torch.zeros((out_bytes + 255) // 256 * 256, dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_out = d_outs[0]
+    gathered = [[torch.empty_like(d_out) for _ in range(world)] for _ in range(2)] if world > 1 else None
+    pending = [None, None]
     st = torch.cuda.current_stream()
 
     def step(k):
-        dec.run_device(streams[k % nbuf][1].data_ptr(), d_out.data_ptr(), N, stream=st.cuda_stream)
-        if world > 1:
-            dist.all_gather(gathered, d_out)   # NCCL over NVLink: packed output bits only
+        b = k & 1
+        if pending[b] is not None:
+            pending[b].wait()              # stream-side wait: buffer b is free again
+            pending[b] = None
+        dec.run_device(streams[k % nbuf][1].data_ptr(), d_outs[b].data_ptr(), N, stream=st.cuda_stream)
+        if world > 1:                      # NCCL over NVLink: packed output bits only, asynchronous
+            pending[b] = dist.all_gather(gathered[b], d_outs[b], async_op=True)
+
+    def drain():
+        for b in (0, 1):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
     # correctness gate inside the bench: BER == 0 at this SNR, and a slice equals the golden model
     step(0)
+    drain()
     torch.cuda.synchronize()
     errs = count_errors_device(torch, d_out, streams[0][0], M, bpp)
     check = {"bit_errors": errs, "ber": errs / M}
@@ -313,6 +327,7 @@ def main():
 
     for k in range(args.warmup):
         step(k)
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -323,6 +338,7 @@ def main():
         e0.record(st)
         for k in range(args.steps):
             step(k)
+        drain()
         e1.record(st)
         torch.cuda.synchronize()
         if world > 1:
@@ -332,7 +348,7 @@ def main():
         # kernel-only duration for the roofline: events bracketing the launch on the launch stream
         kms = []
         for k in range(min(args.steps, 20)):
-            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), d_out.data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True))
+            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), d_outs[0].data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True))
     launches = dec.launch_count() - launches0 - len(kms)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)

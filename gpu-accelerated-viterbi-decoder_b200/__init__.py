@@ -99,11 +99,16 @@ class ViterbiCUDA:
         self.encPack_t = np.float32 if (self.options & CHANNEL_MASK) == FP32 else np.int32
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            lib().vit_destroy(self._h)
+        h = getattr(self, "_h", None)
+        if h and _lib is not None:
+            _lib.vit_destroy(h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     # reference viterbi.cu:63-92
     def getInputSize(self, inputNum):
