@@ -222,18 +222,68 @@ template <int IN> struct Core<MET_B16, IN> {
     static VIT_HD uint32_t plus(uint32_t pm, uint32_t w, uint32_t one) { return pm * one + w; }
     // operand of the opposite branch: (c - b) per half = K2 - w, no borrow because w <= K2 per half
     static VIT_HD uint32_t neg(uint32_t w, uint32_t one) { return w * (0u - one) + K2; }
-    // returns max(partner, own); p* = partner chosen; partner wins ties (reference int16 core,
-    // viterbiACS.cuh:112-119,215-220: __vibmax_s16x2(partner - bm, own + bm) -> pred = (a >= b))
-    static VIT_HD uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool /*own_wins_tie*/) {
+    // Add-compare-select of one packed register = two states.  part/own are the two candidates; the
+    // partner wins ties (reference int16 core, viterbiACS.cuh:112-119,215-220: __vibmax_s16x2(partner - bm,
+    // own + bm) -> pred = (a >= b)).  PTX max.s16x2 + setp.eq on the halves is what __vibmax_s16x2 expands to and
+    // ptxas fuses it into ONE VIMNMX.S16x2 Rd, P0, P1.  The survivor words follow the decision either through
+    // SEL (ALU pipe, acs_sel) or through a predicated IMAD "move" (FMA pipe, acs_mov: `x*one + 0` with the opaque
+    // multiplier is not folded back into SEL), so the selects can be split between the two pipes.
+    static VIT_HD uint32_t acs_sel(uint32_t part, uint32_t own, uint32_t keep_lo, uint32_t src_lo, uint32_t keep_hi,
+                                   uint32_t src_hi, uint32_t& out_lo, uint32_t& out_hi, bool /*own_wins_tie*/) {
 #if defined(__CUDA_ARCH__)
-        return __vibmax_s16x2(part, own, &p_hi, &p_lo);
+        uint32_t v;
+        asm("{.reg .pred pu, pv; \n\t"
+            ".reg .s16 rs0, rs1, rs2, rs3; \n\t"
+            "max.s16x2 %0, %3, %4; \n\t"
+            "mov.b32 {rs0, rs1}, %0; \n\t"
+            "mov.b32 {rs2, rs3}, %3; \n\t"
+            "setp.eq.s16 pv, rs0, rs2; \n\t"
+            "setp.eq.s16 pu, rs1, rs3; \n\t"
+            "selp.b32 %1, %6, %5, pv; \n\t"
+            "selp.b32 %2, %8, %7, pu;} \n\t"
+            : "=r"(v), "=r"(out_lo), "=r"(out_hi)
+            : "r"(part), "r"(own), "r"(keep_lo), "r"(src_lo), "r"(keep_hi), "r"(src_hi));
+        return v;
 #else
+        bool pl, ph;
+        uint32_t v = emu_max(part, own, pl, ph);
+        out_lo = pl ? src_lo : keep_lo; out_hi = ph ? src_hi : keep_hi;
+        return v;
+#endif
+    }
+    static VIT_HD uint32_t acs_mov(uint32_t part, uint32_t own, uint32_t& io_lo, uint32_t src_lo, uint32_t& io_hi,
+                                   uint32_t src_hi, uint32_t one, bool /*own_wins_tie*/) {
+#if defined(__CUDA_ARCH__)
+        uint32_t v;
+        asm("{.reg .pred pu, pv; \n\t"
+            ".reg .s16 rs0, rs1, rs2, rs3; \n\t"
+            "max.s16x2 %0, %3, %4; \n\t"
+            "mov.b32 {rs0, rs1}, %0; \n\t"
+            "mov.b32 {rs2, rs3}, %3; \n\t"
+            "setp.eq.s16 pv, rs0, rs2; \n\t"
+            "setp.eq.s16 pu, rs1, rs3; \n\t"
+            "@pv mad.lo.u32 %1, %5, %7, 0; \n\t"
+            "@pu mad.lo.u32 %2, %6, %7, 0;} \n\t"
+            : "=r"(v), "+r"(io_lo), "+r"(io_hi)
+            : "r"(part), "r"(own), "r"(src_lo), "r"(src_hi), "r"(one));
+        return v;
+#else
+        bool pl, ph;
+        uint32_t v = emu_max(part, own, pl, ph);
+        if (pl) io_lo = src_lo;
+        if (ph) io_hi = src_hi;
+        (void)one;
+        return v;
+#endif
+    }
+#if !defined(__CUDA_ARCH__)
+    static uint32_t emu_max(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi) {
         int16_t al = (int16_t)(part & 0xffff), ah = (int16_t)(part >> 16);
         int16_t bl = (int16_t)(own & 0xffff), bh = (int16_t)(own >> 16);
         p_lo = al >= bl; p_hi = ah >= bh;
         return (uint32_t)(uint16_t)(p_lo ? al : bl) | ((uint32_t)(uint16_t)(p_hi ? ah : bh) << 16);
-#endif
     }
+#endif
     static VIT_HD uint32_t vmin(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
         return __vmins2(a, b);
@@ -255,12 +305,31 @@ template <int IN> struct Core<MET_F16, IN> {
     static VIT_D uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
     static VIT_D uint32_t plus(uint32_t pm, uint32_t w, uint32_t) { return u32(__hadd2(h2(pm), h2(w))); }
     static VIT_D uint32_t neg(uint32_t w, uint32_t) { return u32(__hneg2(h2(w))); }   // folds into HADD2's -operand
-    // own wins ties (reference half2 core, viterbiACS.cuh:146-157,249-256: __hlt2_mask(own, partner))
-    static VIT_D uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool) {
-        __half2 a = h2(part), b = h2(own);
-        p_lo = __hgt(__low2half(a), __low2half(b));
-        p_hi = __hgt(__high2half(a), __high2half(b));
-        return u32(__hmax2(a, b));
+    // own wins ties (reference half2 core, viterbiACS.cuh:146-157,249-256: __hlt2_mask(own, partner)):
+    // partner chosen iff partner > own.  HMNMX2 + HSETP2 (two predicates), then SEL or predicated IMAD.
+    static VIT_D uint32_t acs_sel(uint32_t part, uint32_t own, uint32_t keep_lo, uint32_t src_lo, uint32_t keep_hi,
+                                  uint32_t src_hi, uint32_t& out_lo, uint32_t& out_hi, bool) {
+        uint32_t v;
+        asm("{.reg .pred pl, ph; \n\t"
+            "max.f16x2 %0, %3, %4; \n\t"
+            "setp.gt.f16x2 pl|ph, %3, %4; \n\t"
+            "selp.b32 %1, %6, %5, pl; \n\t"
+            "selp.b32 %2, %8, %7, ph;} \n\t"
+            : "=r"(v), "=r"(out_lo), "=r"(out_hi)
+            : "r"(part), "r"(own), "r"(keep_lo), "r"(src_lo), "r"(keep_hi), "r"(src_hi));
+        return v;
+    }
+    static VIT_D uint32_t acs_mov(uint32_t part, uint32_t own, uint32_t& io_lo, uint32_t src_lo, uint32_t& io_hi,
+                                  uint32_t src_hi, uint32_t one, bool) {
+        uint32_t v;
+        asm("{.reg .pred pl, ph; \n\t"
+            "max.f16x2 %0, %3, %4; \n\t"
+            "setp.gt.f16x2 pl|ph, %3, %4; \n\t"
+            "@pl mad.lo.u32 %1, %5, %7, 0; \n\t"
+            "@ph mad.lo.u32 %2, %6, %7, 0;} \n\t"
+            : "=r"(v), "+r"(io_lo), "+r"(io_hi)
+            : "r"(part), "r"(own), "r"(src_lo), "r"(src_hi), "r"(one));
+        return v;
     }
     static VIT_D uint32_t vmin(uint32_t a, uint32_t b) { return u32(__hmin2(h2(a), h2(b))); }
     static VIT_D uint32_t sub(uint32_t a, uint32_t m) { return u32(__hsub2(h2(a), h2(m))); }
@@ -268,10 +337,25 @@ template <int IN> struct Core<MET_F16, IN> {
 #else
     static uint32_t plus(uint32_t pm, uint32_t w, uint32_t) { EmuH2 a = emu_h2_unpack(pm), b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{a.lo + b.lo, a.hi + b.hi}); }
     static uint32_t neg(uint32_t w, uint32_t) { EmuH2 b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{-b.lo, -b.hi}); }
-    static uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool) {
+    static uint32_t emu_max(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi) {
         EmuH2 a = emu_h2_unpack(part), b = emu_h2_unpack(own);
         p_lo = a.lo > b.lo; p_hi = a.hi > b.hi;
         return emu_h2_pack(EmuH2{p_lo ? a.lo : b.lo, p_hi ? a.hi : b.hi});
+    }
+    static uint32_t acs_sel(uint32_t part, uint32_t own, uint32_t keep_lo, uint32_t src_lo, uint32_t keep_hi,
+                            uint32_t src_hi, uint32_t& out_lo, uint32_t& out_hi, bool) {
+        bool pl, ph;
+        uint32_t v = emu_max(part, own, pl, ph);
+        out_lo = pl ? src_lo : keep_lo; out_hi = ph ? src_hi : keep_hi;
+        return v;
+    }
+    static uint32_t acs_mov(uint32_t part, uint32_t own, uint32_t& io_lo, uint32_t src_lo, uint32_t& io_hi,
+                            uint32_t src_hi, uint32_t, bool) {
+        bool pl, ph;
+        uint32_t v = emu_max(part, own, pl, ph);
+        if (pl) io_lo = src_lo;
+        if (ph) io_hi = src_hi;
+        return v;
     }
     static uint32_t vmin(uint32_t a, uint32_t b) { EmuH2 x = emu_h2_unpack(a), y = emu_h2_unpack(b); return emu_h2_pack(EmuH2{x.lo < y.lo ? x.lo : y.lo, x.hi < y.hi ? x.hi : y.hi}); }
     static uint32_t sub(uint32_t a, uint32_t m) { return plus(a, neg(m, 1), 1); }
@@ -286,12 +370,39 @@ template <int IN> struct Core<MET_B32, IN> {
     static VIT_HD uint32_t plus(uint32_t pm, uint32_t w, uint32_t one) { return pm * one + w; }      // IMAD
     static VIT_HD uint32_t neg(uint32_t w, uint32_t one) { return w * (0u - one); }
     // partner wins ties except where the reference's phase-0 rule makes the odd predecessor win
-    // (viterbiACS.cuh:136-142: both selfPM compares are "odd-candidate >= even-candidate")
-    static VIT_HD uint32_t maxsel(uint32_t part, uint32_t own, bool& p_lo, bool& p_hi, bool own_wins_tie) {
-        int a = (int)part, b = (int)own;
-        bool p = own_wins_tie ? (a > b) : (a >= b);
-        p_lo = p; p_hi = p;
+    // (viterbiACS.cuh:136-142: both selfPM compares are "odd-candidate >= even-candidate").
+    // One state per register: ISETP, metric select on the ALU pipe, survivor select on either pipe.
+    template <bool OWN_WINS>
+    static VIT_HD uint32_t acs1_sel(uint32_t part, uint32_t own, uint32_t keep, uint32_t src, uint32_t& out) {
+        const int a = (int)part, b = (int)own;
+        const bool p = OWN_WINS ? (a > b) : (a >= b);
+        out = p ? src : keep;
         return (uint32_t)(p ? a : b);
+    }
+    template <bool OWN_WINS>
+    static VIT_HD uint32_t acs1_mov(uint32_t part, uint32_t own, uint32_t& io, uint32_t src, uint32_t one) {
+#if defined(__CUDA_ARCH__)
+        uint32_t v;
+        if (OWN_WINS)
+            asm("{.reg .pred p; \n\t"
+                "setp.gt.s32 p, %2, %3; \n\t"
+                "selp.b32 %0, %2, %3, p; \n\t"
+                "@p mad.lo.u32 %1, %4, %5, 0;} \n\t"
+                : "=r"(v), "+r"(io) : "r"(part), "r"(own), "r"(src), "r"(one));
+        else
+            asm("{.reg .pred p; \n\t"
+                "setp.ge.s32 p, %2, %3; \n\t"
+                "selp.b32 %0, %2, %3, p; \n\t"
+                "@p mad.lo.u32 %1, %4, %5, 0;} \n\t"
+                : "=r"(v), "+r"(io) : "r"(part), "r"(own), "r"(src), "r"(one));
+        return v;
+#else
+        const int a = (int)part, b = (int)own;
+        const bool p = OWN_WINS ? (a > b) : (a >= b);
+        if (p) io = src;
+        (void)one;
+        return (uint32_t)(p ? a : b);
+#endif
     }
     static VIT_HD uint32_t vmin(uint32_t a, uint32_t b) { return (uint32_t)((int)a < (int)b ? (int)a : (int)b); }
     static VIT_HD uint32_t sub(uint32_t a, uint32_t m) { return a - m; }
@@ -321,11 +432,13 @@ VIT_HD uint32_t cand(uint32_t metric, const Operands& o) {
 }
 
 // one trellis stage at phase P (static).  lane bits are the low 3 bits of the lane id.
+// Survivor selects alternate between the SEL form (ALU pipe) and the predicated-IMAD form (FMA pipe).
 template <int MET, int IN, int P>
 VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
     using C = Core<MET, IN>;
     constexpr int KIND = stage_kind<MET>(P);
     constexpr int BIT = stage_bit(P);
+    const uint32_t one = ops.one;
     if constexpr (KIND == KIND_LANE) {
         constexpr int XM = 1 << BIT;
         uint32_t ppm[LaneState<MET>::NPM], ppp[8];
@@ -336,23 +449,22 @@ VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
         if constexpr (C::PACKED) {
 #define VIT_LANE_PACKED(r)                                                                        \
     {                                                                                             \
-        bool pl, ph;                                                                              \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                             \
-        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                               \
-        s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
-        s.pp[r] = pl ? ppp[r] : s.pp[r];                                                          \
-        s.pp[r + 4] = ph ? ppp[r + 4] : s.pp[r + 4];                                              \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                                \
+        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                                  \
+        if constexpr ((r & 1) == 0)                                                               \
+            s.pm[r] = C::acs_sel(pc, oc, s.pp[r], ppp[r], s.pp[r + 4], ppp[r + 4], s.pp[r], s.pp[r + 4], false); \
+        else                                                                                      \
+            s.pm[r] = C::acs_mov(pc, oc, s.pp[r], ppp[r], s.pp[r + 4], ppp[r + 4], one, false);   \
     }
             VIT_LANE_PACKED(0) VIT_LANE_PACKED(1) VIT_LANE_PACKED(2) VIT_LANE_PACKED(3)
 #undef VIT_LANE_PACKED
         } else {
 #define VIT_LANE_B32(r)                                                                           \
     {                                                                                             \
-        bool pl, ph;                                                                              \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                             \
-        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                               \
-        s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
-        s.pp[r] = pl ? ppp[r] : s.pp[r];                                                          \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                                \
+        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                                  \
+        if constexpr ((r & 1) == 0) s.pm[r] = C::template acs1_sel<false>(pc, oc, s.pp[r], ppp[r], s.pp[r]); \
+        else s.pm[r] = C::template acs1_mov<false>(pc, oc, s.pp[r], ppp[r], one);                 \
     }
             VIT_LANE_B32(0) VIT_LANE_B32(1) VIT_LANE_B32(2) VIT_LANE_B32(3)
             VIT_LANE_B32(4) VIT_LANE_B32(5) VIT_LANE_B32(6) VIT_LANE_B32(7)
@@ -362,33 +474,27 @@ VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
         // packed cores, phase 0: the two predecessors are the two halves of the same register
 #define VIT_HALF(r)                                                                               \
     {                                                                                             \
-        bool pl, ph;                                                                              \
         uint32_t sw = prmt(s.pm[r], 0, 0x1032);                                                   \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                             \
-        uint32_t pc = cand<C, bm_type(r, P), true>(sw, ops);                                   \
-        s.pm[r] = C::maxsel(pc, oc, pl, ph, false);                                               \
-        uint32_t a = s.pp[r], b = s.pp[r + 4];                                                    \
-        s.pp[r] = pl ? b : a;                                                                     \
-        s.pp[r + 4] = ph ? a : b;                                                                 \
+        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                                \
+        uint32_t pc = cand<C, bm_type(r, P), true>(sw, ops);                                      \
+        const uint32_t a = s.pp[r], b = s.pp[r + 4];                                              \
+        s.pm[r] = C::acs_sel(pc, oc, a, b, b, a, s.pp[r], s.pp[r + 4], false);                    \
     }
         VIT_HALF(0) VIT_HALF(1) VIT_HALF(2) VIT_HALF(3)
 #undef VIT_HALF
     } else {
-        // register-local butterfly on register-index bit BIT
+        // register-local butterfly on register-index bit BIT: the even register's survivors use the SEL
+        // form (new registers), the odd register's the in-place predicated form
         if constexpr (C::PACKED) {
 #define VIT_REG_PACKED(ra)                                                                        \
     if constexpr (((ra >> BIT) & 1) == 0) {                                                       \
         constexpr int rb = ra | (1 << BIT);                                                       \
-        bool al, ah, bl, bh;                                                                      \
-        uint32_t ea = s.pm[ra], eb = s.pm[rb];                                                    \
-        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, ops),                        \
-                                cand<C, bm_type(ra, P), false>(ea, ops), al, ah, false);       \
-        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, ops),                        \
-                                cand<C, bm_type(rb, P), false>(eb, ops), bl, bh, false);       \
-        s.pm[ra] = na; s.pm[rb] = nb;                                                             \
-        uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb], pa1 = s.pp[ra + 4], pb1 = s.pp[rb + 4];          \
-        s.pp[ra] = al ? pb0 : pa0; s.pp[rb] = bl ? pa0 : pb0;                                     \
-        s.pp[ra + 4] = ah ? pb1 : pa1; s.pp[rb + 4] = bh ? pa1 : pb1;                             \
+        const uint32_t ea = s.pm[ra], eb = s.pm[rb];                                              \
+        const uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb], pa1 = s.pp[ra + 4], pb1 = s.pp[rb + 4];    \
+        s.pm[ra] = C::acs_sel(cand<C, bm_type(ra, P), true>(eb, ops), cand<C, bm_type(ra, P), false>(ea, ops), \
+                              pa0, pb0, pa1, pb1, s.pp[ra], s.pp[ra + 4], false);                 \
+        s.pm[rb] = C::acs_mov(cand<C, bm_type(rb, P), true>(ea, ops), cand<C, bm_type(rb, P), false>(eb, ops), \
+                              s.pp[rb], pa0, s.pp[rb + 4], pa1, one, false);                      \
     }
             VIT_REG_PACKED(0) VIT_REG_PACKED(1) VIT_REG_PACKED(2) VIT_REG_PACKED(3)
 #undef VIT_REG_PACKED
@@ -399,15 +505,12 @@ VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
 #define VIT_REG_B32(ra)                                                                           \
     if constexpr (((ra >> BIT) & 1) == 0) {                                                       \
         constexpr int rb = ra | (1 << BIT);                                                       \
-        bool al, ah, bl, bh;                                                                      \
-        uint32_t ea = s.pm[ra], eb = s.pm[rb];                                                    \
-        uint32_t na = C::maxsel(cand<C, bm_type(ra, P), true>(eb, ops),                        \
-                                cand<C, bm_type(ra, P), false>(ea, ops), al, ah, false);       \
-        uint32_t nb = C::maxsel(cand<C, bm_type(rb, P), true>(ea, ops),                        \
-                                cand<C, bm_type(rb, P), false>(eb, ops), bl, bh, ODD_WINS);    \
-        s.pm[ra] = na; s.pm[rb] = nb;                                                             \
-        uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb];                                                  \
-        s.pp[ra] = al ? pb0 : pa0; s.pp[rb] = bl ? pa0 : pb0;                                     \
+        const uint32_t ea = s.pm[ra], eb = s.pm[rb];                                              \
+        const uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb];                                            \
+        s.pm[ra] = C::template acs1_sel<false>(cand<C, bm_type(ra, P), true>(eb, ops),            \
+                                               cand<C, bm_type(ra, P), false>(ea, ops), pa0, pb0, s.pp[ra]); \
+        s.pm[rb] = C::template acs1_mov<ODD_WINS>(cand<C, bm_type(rb, P), true>(ea, ops),         \
+                                                  cand<C, bm_type(rb, P), false>(eb, ops), s.pp[rb], pa0, one); \
     }
             VIT_REG_B32(0) VIT_REG_B32(1) VIT_REG_B32(2) VIT_REG_B32(3)
             VIT_REG_B32(4) VIT_REG_B32(5) VIT_REG_B32(6) VIT_REG_B32(7)
