@@ -287,31 +287,42 @@ def main():
         if pad:
             packed = torch.cat([packed, torch.zeros(pad, dtype=torch.uint8, device=dev)])
         streams.append((bits if k == 0 else None, packed))
-    # two output buffers: the NCCL gather of step k overlaps the decode of step k+1
-    d_outs = [torch.zeros((out_bytes + 255) // 256 * 256, dtype=torch.uint8, device=dev) for _ in range(2)]
-    d_out = d_outs[0]
-    gathered = [[torch.empty_like(d_out) for _ in range(world)] for _ in range(2)] if world > 1 else None
+    # Outputs go to a ring of 2 x GB slots.  For N > 1 the packed output bits of GB consecutive steps are
+    # gathered with ONE NCCL all_gather_into_tensor (flat buffers, no staging copies) that runs asynchronously
+    # while the next GB decodes fill the other half of the ring: the collective is latency-bound at this size,
+    # so it is batched, and it never sits on the decode stream's critical path.
+    GB = 8 if world > 1 else 1
+    out_stride = (out_bytes + 255) // 256 * 256
+    ring = torch.zeros(2 * GB * out_stride, dtype=torch.uint8, device=dev)
+    d_out = ring[:out_stride]
+    gathered = [torch.empty(world * GB * out_stride, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     pending = [None, None]
     st = torch.cuda.current_stream()
 
-    def step(k):
-        b = k & 1
-        if pending[b] is not None:
-            pending[b].wait()              # stream-side wait: buffer b is free again
-            pending[b] = None
-        dec.run_device(streams[k % nbuf][1].data_ptr(), d_outs[b].data_ptr(), N, stream=st.cuda_stream)
-        if world > 1:                      # NCCL over NVLink: packed output bits only, asynchronous
-            pending[b] = dist.all_gather(gathered[b], d_outs[b], async_op=True)
+    def gather_half(h):
+        pending[h] = dist.all_gather_into_tensor(gathered[h], ring[h * GB * out_stride:(h + 1) * GB * out_stride], async_op=True)
 
-    def drain():
-        for b in (0, 1):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
+    def step(k):
+        slot = k % (2 * GB)
+        h = slot // GB
+        if slot % GB == 0 and pending[h] is not None:
+            pending[h].wait()              # stream-side wait: this half of the ring is free again
+            pending[h] = None
+        dec.run_device(streams[k % nbuf][1].data_ptr(), ring[slot * out_stride:].data_ptr(), N, stream=st.cuda_stream)
+        if world > 1 and slot % GB == GB - 1:
+            gather_half(h)                 # NCCL over NVLink: packed output bits only
+
+    def drain(last_k=None):
+        if world > 1 and last_k is not None and (last_k % GB) != GB - 1:
+            gather_half((last_k % (2 * GB)) // GB)      # partial group at the end of the run
+        for h in (0, 1):
+            if pending[h] is not None:
+                pending[h].wait()
+                pending[h] = None
 
     # correctness gate inside the bench: BER == 0 at this SNR, and a slice equals the golden model
     step(0)
-    drain()
+    drain(0)
     torch.cuda.synchronize()
     errs = count_errors_device(torch, d_out, streams[0][0], M, bpp)
     check = {"bit_errors": errs, "ber": errs / M}
@@ -327,7 +338,7 @@ def main():
 
     for k in range(args.warmup):
         step(k)
-    drain()
+    drain(args.warmup - 1)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -338,7 +349,7 @@ def main():
         e0.record(st)
         for k in range(args.steps):
             step(k)
-        drain()
+        drain(args.steps - 1)
         e1.record(st)
         torch.cuda.synchronize()
         if world > 1:
@@ -348,7 +359,7 @@ def main():
         # kernel-only duration for the roofline: events bracketing the launch on the launch stream
         kms = []
         for k in range(min(args.steps, 20)):
-            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), d_outs[0].data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True))
+            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), d_out.data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True))
     launches = dec.launch_count() - launches0 - len(kms)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -396,7 +407,7 @@ def main():
             "dtype": {0x00: "int32", 0x10: "int16x2", 0x20: "f16x2"}[options & 0xF0], "data": "synthetic",
             "config": {"workload": args.workload, "message_bits": n_bits, "options": "0x%03x" % options, "snr_db": snr,
                        "segments": 6400, "streams_per_step_per_gpu": 1, "l2": "inputs rotate over %d distinct device buffers (%.0f MB > 126 MB L2)" % (nbuf, nbuf * in_bytes / 1e6),
-                       "parallelism": "stream-sharded x%d, NCCL all_gather of packed output bits" % world if world > 1 else "single GPU"},
+                       "parallelism": ("stream-sharded x%d, one NCCL all_gather_into_tensor of packed output bits per %d steps, overlapped" % (world, GB)) if world > 1 else "single GPU"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
             "kernel": {"ms": kernel_ms, "gbps": k_gbps, "regs": info["regs"], "smem_bytes": info["smem_bytes"],
                        "grid": [1600, 1, 1], "block": 32},

@@ -59,6 +59,8 @@ def lib():
         L.vit_launch_count.restype, L.vit_launch_count.argtypes = C.c_ulonglong, [vp]
         L.vit_set_segments.restype, L.vit_set_segments.argtypes = C.c_int, [vp, C.c_uint]
         L.vit_last_error.restype, L.vit_last_error.argtypes = C.c_char_p, []
+        L.vit_synth_device.restype = C.c_int
+        L.vit_synth_device.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -84,6 +86,13 @@ def parse_options(input="h", metric="b32", output="b32", comp="reg"):
     o = {"b16": O_B16, "b32": O_B32}[output]
     c = {"REG": REG, "reg": REG, "DPX": DPX, "dpx": DPX}[comp]
     return i | m | o | c
+
+
+def synth_device(input_type, n_bits, packed_ptr, bits_ptr=None, seed=1, amp=0, sigma=0.0, zero=False, stream=0):
+    """Device-side synthetic received stream (vit_synth_device): the GPU twin of the reference harness's host
+    source/encoder/noise/packer chain.  packed_ptr must hold whole 32-bit packs."""
+    _check(lib().vit_synth_device(int(input_type), int(n_bits), int(seed), int(amp), float(sigma), int(bool(zero)),
+                                  packed_ptr, bits_ptr, stream))
 
 
 class ViterbiCUDA:

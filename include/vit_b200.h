@@ -87,6 +87,15 @@ unsigned long long vit_launch_count(const vit_handle* h);
 /* test hook: number of stream segments (reference: 6400, viterbi.cu:19); 0 restores 6400 */
 int vit_set_segments(vit_handle* h, unsigned segments);
 
+/* Device-side synthetic channel source (new): the GPU twin of the reference harness's host
+ * chain RandBitGen | ConvolutionalEncoder | AddNoise | SoftDecisionPacker (src/viterbiDF.h:20-167), counter
+ * based and integer only so a CPU twin reproduces it bit for bit.  Writes the packed received stream for
+ * n_bits message bits to packed_d (whole 32-bit packs) and, if bits_d != NULL, one byte per message bit.
+ * amp = symbol amplitude in quantiser units (<= 0: default per input type), sigma = noise sd / amp,
+ * zero != 0: all-zero symbols (tie stress). */
+int vit_synth_device(int input_type, size_t n_bits, unsigned seed, int amp, double sigma, int zero,
+                     void* packed_d, void* bits_d, void* cuda_stream);
+
 const char* vit_last_error(void);
 
 #ifdef __cplusplus

@@ -165,7 +165,15 @@ def _splitmix64(x):
     return z ^ (z >> np.uint64(31))
 
 
-def make_channel_det(n_bits, input_type, seed=1, amp=None, sigma=0.0, zero=False):
+def hash_bits(seed, n_bits):
+    """Message bits as a counter hash: bit i = top bit of splitmix64(i + seed * 0x9E3779B97F4A7C15 ... ).
+    Twin of the device generator (csrc/vit_synth.cu) -- any bit can be produced independently."""
+    with np.errstate(over="ignore"):
+        h = _splitmix64(np.arange(n_bits, dtype=np.uint64) + np.uint64(seed) * np.uint64(0xD1B54A32D192ED03))
+    return (h >> np.uint64(63)).astype(np.uint8)
+
+
+def make_channel_det(n_bits, input_type, seed=1, amp=None, sigma=0.0, zero=False, bits_source="prbs"):
     """Bit-reproducible channel (integer arithmetic only, no libm, no numpy RNG): PRBS-31 message,
     K=7 encoder, symbol = +-amp + noise in Q8 fixed point, noise = (sum of four 16-bit uniforms from
     splitmix64, centred) scaled to a standard deviation of about sigma*amp, then the reference's
@@ -173,7 +181,7 @@ def make_channel_det(n_bits, input_type, seed=1, amp=None, sigma=0.0, zero=False
     Returns (bits, packed, input_num)."""
     if amp is None:
         amp = {HARD: 64, SOFT4: 3, SOFT8: 40, SOFT16: 9000, FP32: 48}[input_type]
-    bits = prbs31(0x7FFFFFFF ^ seed, n_bits)
+    bits = prbs31(0x7FFFFFFF ^ seed, n_bits) if bits_source == "prbs" else hash_bits(seed, n_bits)
     coded = encode(bits).astype(np.int64)
     per = {HARD: 32, SOFT4: 8, SOFT8: 4, SOFT16: 2, FP32: 1}[input_type]
     nsym = coded.size

@@ -113,3 +113,105 @@ def test_config3_f16_256M_mismatch_vs_b32(V, O):
     qq, rr = divmod(P, 6400)
     a, bnd = qq * 3000 + min(3000, rr), qq * 3016 + min(3016, rr)
     assert np.array_equal(words.cpu().numpy().view(np.uint16)[a:bnd], seg_out[a:bnd])
+
+
+def test_no_writes_outside_the_output_and_no_dependence_on_bytes_past_the_input(V, O):
+    """compute-sanitizer is closed on this pool, so bounds are checked with canaries: the decoder must
+    write exactly getOutputSize bytes and its result must not depend on what follows the input buffer."""
+    import torch
+    for opt, n in ((0x112, 64 + 16 * 6400 * 3 + 16 * 5), (0x011, 64 + 32 * 7001), (0x100, 64 + 16 * 12801), (0x004, 64 + 32 * 900)):
+        it = opt & 0xF
+        bits, packed, N = O.make_channel_det(n, it, seed=77, sigma=0.9)
+        dec = V.ViterbiCUDA(opt)
+        in_b, out_b = dec.getInputSize(N), dec.getOutputSize(N)
+        exp = O.decode(opt, packed, N)
+        raw = torch.from_numpy(packed.view(np.uint8)[:in_b].copy())
+        outs = []
+        for fill in (0x00, 0xFF):
+            d_in = torch.full((in_b + 4096,), fill, dtype=torch.uint8, device="cuda")
+            d_in[:in_b] = raw.cuda()
+            d_out = torch.full((out_b + 512,), 0xA5, dtype=torch.uint8, device="cuda")
+            dec.run_device(d_in.data_ptr(), d_out.data_ptr(), N)
+            torch.cuda.synchronize()
+            h = d_out.cpu().numpy()
+            assert np.all(h[out_b:] == 0xA5), hex(opt)
+            outs.append(h[:out_b].copy())
+        assert np.array_equal(outs[0], outs[1]), hex(opt)
+        assert np.array_equal(outs[0].view(dec.decPack_t), exp), hex(opt)
+        dec.close()
+
+
+def test_host_harness_binary(V):
+    """The ./main-style harness (host/main.cpp, reference flags) decodes without bit errors at the
+    reference's default operating points."""
+    import os
+    import re
+    import subprocess
+    from vit_testlib import PKG_DIR
+    exe = os.path.join(PKG_DIR, "host", "main")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(PKG_DIR, "host")])
+    for args in (["-n", "1000000", "-s", "5.5", "-m", "b32", "-i", "h", "--seed", "1"],
+                 ["-n", "2000000", "-i", "s4", "-m", "b16", "-o", "b32", "--seed", "2", "-v"],
+                 ["-n", "2000000", "-i", "s8", "-m", "f16", "-o", "b16", "-s", "3", "--seed", "3", "--prbs", "--reps", "3"],
+                 ["-n", "1000000", "-i", "f", "-m", "b32", "-c", "dpx", "--seed", "4"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-500:]
+        m = re.search(r"BEN: (\d+)", out.stdout)
+        assert m and int(m.group(1)) == 0, out.stdout[-500:]
+        assert "Gb/s" in out.stdout
+    # the reference's own validity message and exit code for b16 x s16 (main.cpp:26-29)
+    out = subprocess.run([exe, "-i", "s16", "-m", "b16"], capture_output=True, text=True)
+    assert out.returncode != 0 and "16-bit metric does not support 16-bit soft decision input" in out.stderr
+
+
+def test_smoke_entry_point():
+    import importlib
+    import sys
+    from vit_testlib import ROOT
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    g = importlib.import_module("__graft_entry__")
+    g.smoke()
+
+
+def test_device_synthetic_source_matches_cpu_twin(V, O):
+    """vit_synth_device (GPU twin of viterbiDF.h's source/encoder/noise/packer) is bit-identical to the numpy
+    twin, for every input type, with and without noise."""
+    import torch
+    n = 50_000 + 3
+    for it in range(5):
+        for sigma in (0.0, 0.8):
+            bits, packed, N = O.make_channel_det(n, it, seed=9, sigma=sigma, bits_source="hash")
+            nwords = packed.size if it != 4 else packed.size // 2
+            d_p = torch.zeros(packed.nbytes + 64, dtype=torch.uint8, device="cuda")
+            d_b = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            V.synth_device(it, n, d_p.data_ptr(), d_b.data_ptr(), seed=9, sigma=sigma)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_b.cpu().numpy(), bits), it
+            got = d_p.cpu().numpy()[:packed.nbytes]
+            assert np.array_equal(got, packed.view(np.uint8)), (it, sigma)
+
+
+def test_device_source_feeds_decoder(V, O):
+    """64 Mbit generated and decoded entirely on the device: noiseless round trip is error free."""
+    import torch
+    opt, n = 0x012, 64_000_000
+    dec = V.ViterbiCUDA(opt)
+    N = 2 * n
+    d_p = torch.zeros(dec.getInputSize(N) + 256, dtype=torch.uint8, device="cuda")
+    d_b = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    V.synth_device(O.SOFT8, n, d_p.data_ptr(), d_b.data_ptr(), seed=5, sigma=0.3)
+    d_o = torch.zeros(dec.getOutputSize(N), dtype=torch.uint8, device="cuda")
+    dec.run_device(d_p.data_ptr(), d_o.data_ptr(), N)
+    torch.cuda.synchronize()
+    M = dec.getMessageLen(N)
+    w = d_o.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    sh = torch.arange(31, -1, -1, device="cuda", dtype=torch.int64)
+    errs = 0
+    for a in range(0, M // 32, 1 << 20):
+        b = min(M // 32, a + (1 << 20))
+        db = ((w[a:b].unsqueeze(1) >> sh) & 1).reshape(-1).to(torch.uint8)
+        errs += int((db != d_b[26 + 32 * a:26 + 32 * b]).sum().item())
+    assert errs == 0
+    dec.close()
