@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s4_b16_o32_32M", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=1, help="independent codeword streams decoded per step by ONE launch (config 5 shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -279,20 +280,28 @@ def main():
     in_bytes, out_bytes = dec.getInputSize(N), dec.getOutputSize(N)
 
     # distinct input streams rotated step to step so that the working set exceeds L2 (126 MB)
-    nbuf = max(2, min(8, int(300e6 // in_bytes) + 1)) if in_bytes < 300e6 else 1
+    S = max(1, args.streams)
+    in_stride = (in_bytes + 255) // 256 * 256
+    nbuf = max(2, min(8, int(300e6 // (in_bytes * S)) + 1)) if in_bytes * S < 300e6 else 1
     streams = []
     for k in range(nbuf):
-        bits, packed, _ = make_stream_device(torch, n_bits, it, snr, 1000 * rank + k + 1, dev)
-        pad = (-packed.numel()) % 256
-        if pad:
-            packed = torch.cat([packed, torch.zeros(pad, dtype=torch.uint8, device=dev)])
-        streams.append((bits if k == 0 else None, packed))
+        parts, bits0 = [], None
+        for j in range(S):
+            bits, packed, _ = make_stream_device(torch, n_bits, it, snr, 1000 * rank + k * S + j + 1, dev)
+            pad = in_stride - packed.numel()
+            if pad:
+                packed = torch.cat([packed, torch.zeros(pad, dtype=torch.uint8, device=dev)])
+            parts.append(packed)
+            if k == 0 and j == 0:
+                bits0 = bits
+        streams.append((bits0, torch.cat(parts) if S > 1 else parts[0]))
     # Outputs go to a ring of 2 x GB slots.  For N > 1 the packed output bits of GB consecutive steps are
     # gathered with ONE NCCL all_gather_into_tensor (flat buffers, no staging copies) that runs asynchronously
     # while the next GB decodes fill the other half of the ring: the collective is latency-bound at this size,
     # so it is batched, and it never sits on the decode stream's critical path.
     GB = 8 if world > 1 else 1
-    out_stride = (out_bytes + 255) // 256 * 256
+    out_stride1 = (out_bytes + 255) // 256 * 256          # per stream
+    out_stride = out_stride1 * S                            # per step
     ring = torch.zeros(2 * GB * out_stride, dtype=torch.uint8, device=dev)
     d_out = ring[:out_stride]
     gathered = [torch.empty(world * GB * out_stride, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
@@ -308,7 +317,8 @@ def main():
         if slot % GB == 0 and pending[h] is not None:
             pending[h].wait()              # stream-side wait: this half of the ring is free again
             pending[h] = None
-        dec.run_device(streams[k % nbuf][1].data_ptr(), ring[slot * out_stride:].data_ptr(), N, stream=st.cuda_stream)
+        dec.run_device(streams[k % nbuf][1].data_ptr(), ring[slot * out_stride:].data_ptr(), N, stream=st.cuda_stream,
+                       nstreams=S, in_stride=in_stride, out_stride=out_stride1)
         if world > 1 and slot % GB == GB - 1:
             gather_half(h)                 # NCCL over NVLink: packed output bits only
 
@@ -328,7 +338,7 @@ def main():
     check = {"bit_errors": errs, "ber": errs / M}
     if rank == 0:
         from oracle import oracle as O
-        host_in = streams[0][1][:in_bytes].cpu().numpy()
+        host_in = streams[0][1][:in_bytes].cpu().numpy()   # stream 0 of the step
         seg = O.decode(options, host_in, N, segs=(1000, 1016))
         P = M // bpp
         q, r = divmod(P, 6400)
@@ -359,19 +369,20 @@ def main():
         # kernel-only duration for the roofline: events bracketing the launch on the launch stream
         kms = []
         for k in range(min(args.steps, 20)):
-            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), d_out.data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True))
+            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), ring.data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True,
+                                      nstreams=S, in_stride=in_stride, out_stride=out_stride1))
     launches = dec.launch_count() - launches0 - len(kms)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = M * world / (ms_step * 1e6)                       # whole-job decoded Gb/s
+    value = M * S * world / (ms_step * 1e6)                   # whole-job decoded Gb/s
     kernel_ms = statistics.mean(kms)
 
     # e2e through the public host-buffer call (pinned host memory), copies inside the timed region
     e2e = None
-    if not args.no_e2e and in_bytes < 8e9:
+    if not args.no_e2e and in_bytes < 8e9 and S == 1:
         h_in = [s[1][:in_bytes].cpu().pin_memory() for s in streams[:min(nbuf, 4)]]
         h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
         h_out_np = h_out.numpy().view(dec.decPack_t)
@@ -398,19 +409,19 @@ def main():
         wi_per_bit = 6 if (options & 0xF0) == 0 else 3          # int32 core 6, packed cores 3
         issue_peak_nominal = N_SM * 4 * sm_max_mhz * 1e6 / wi_per_bit / 1e9
         issue_peak_at_clock = N_SM * 4 * f_mhz * 1e6 / wi_per_bit / 1e9
-        k_gbps = M / (kernel_ms * 1e6)
-        alg_bytes = M * (BYTES_PER_BIT_IN[it] + 0.125)
+        k_gbps = M * S / (kernel_ms * 1e6)
+        alg_bytes = M * S * (BYTES_PER_BIT_IN[it] + 0.125)
         info = dec.kernel_info()
         line = {
             "metric": "decoded Gb/s", "value": value, "unit": "Gb/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0x00: "int32", 0x10: "int16x2", 0x20: "f16x2"}[options & 0xF0], "data": "synthetic",
             "config": {"workload": args.workload, "message_bits": n_bits, "options": "0x%03x" % options, "snr_db": snr,
-                       "segments": 6400, "streams_per_step_per_gpu": 1, "l2": "inputs rotate over %d distinct device buffers (%.0f MB > 126 MB L2)" % (nbuf, nbuf * in_bytes / 1e6),
+                       "segments": 6400, "streams_per_step_per_gpu": S, "l2": "inputs rotate over %d distinct device buffers (%.0f MB > 126 MB L2)" % (nbuf, nbuf * in_bytes / 1e6),
                        "parallelism": ("stream-sharded x%d, one NCCL all_gather_into_tensor of packed output bits per %d steps, overlapped" % (world, GB)) if world > 1 else "single GPU"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
             "kernel": {"ms": kernel_ms, "gbps": k_gbps, "regs": info["regs"], "smem_bytes": info["smem_bytes"],
-                       "grid": [1600, 1, 1], "block": 32},
+                       "grid": [1600, S, 1], "block": 32},
             "roofline": {"bound": "issue", "achieved": k_gbps, "peak": issue_peak_nominal, "unit": "Gb/s decoded", "frac": k_gbps / issue_peak_nominal,
                          "peak_at_measured_clock": issue_peak_at_clock, "frac_at_measured_clock": k_gbps / issue_peak_at_clock,
                          "how": "ACS-op roofline: 192 add/compare-select ops per decoded bit = %d warp-instructions; peak = 148 SM x 4 issue/clk x f_SM / that" % wi_per_bit,
