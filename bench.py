@@ -49,6 +49,9 @@ WORKLOADS = {
     "s8_b16_o32_256M": (0x012, 256_000_000, 15.0),  # configs[4] per-stream shape
 }
 BYTES_PER_BIT_IN = {0: 0.25, 1: 1.0, 2: 2.0, 3: 4.0, 4: 8.0}
+# DRAM traffic per launch from the committed ncu --set full captures (profiles/): the channel words are read exactly
+# once (32.0 MB); the 4 MB of decoded packs are still in L2 when the kernel ends (dram__bytes_write = 0).
+NCU_DRAM_BYTES = {("s4_b16_o32_32M", 1): 32.0e6}
 N_SM = 148
 
 
@@ -424,10 +427,11 @@ def main():
                        "grid": [1600, S, 1], "block": 32},
             "roofline": {"bound": "issue", "achieved": k_gbps, "peak": issue_peak_nominal, "unit": "Gb/s decoded", "frac": k_gbps / issue_peak_nominal,
                          "peak_at_measured_clock": issue_peak_at_clock, "frac_at_measured_clock": k_gbps / issue_peak_at_clock,
+                         "achieved_acs_warp_inst_per_s": k_gbps * 1e9 * wi_per_bit, "peak_warp_inst_per_s": N_SM * 4 * sm_max_mhz * 1e6,
                          "how": "ACS-op roofline: 192 add/compare-select ops per decoded bit = %d warp-instructions; peak = 148 SM x 4 issue/clk x f_SM / that" % wi_per_bit,
-                         "traffic": None},
+                         "traffic": NCU_DRAM_BYTES.get((args.workload, S)), "traffic_source": "profiles/r1_v4_ncu_core_0x011.txt (dram__bytes_read+write per launch, one ncu --set full capture)" if NCU_DRAM_BYTES.get((args.workload, S)) else None},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e6), "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / (kernel_ms * 1e6) / hbm_peak, "peak_kind": peak_kind, "traffic": None,
+                             "frac": alg_bytes / (kernel_ms * 1e6) / hbm_peak, "peak_kind": peak_kind, "traffic": NCU_DRAM_BYTES.get((args.workload, S)),
                              "algorithmic_bytes_per_launch": alg_bytes},
         }
         if not args.no_cpu_baseline and world == 1:
