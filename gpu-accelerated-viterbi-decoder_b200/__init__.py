@@ -59,6 +59,12 @@ def lib():
         L.vit_launch_count.restype, L.vit_launch_count.argtypes = C.c_ulonglong, [vp]
         L.vit_set_segments.restype, L.vit_set_segments.argtypes = C.c_int, [vp, C.c_uint]
         L.vit_last_error.restype, L.vit_last_error.argtypes = C.c_char_p, []
+        L.vit_count_errors_device.restype = C.c_int
+        L.vit_count_errors_device.argtypes = [C.c_int, vp, vp, sz, C.POINTER(C.c_ulonglong), vp]
+        L.vit_dev_alloc.restype, L.vit_dev_alloc.argtypes = C.c_int, [C.POINTER(vp), sz]
+        L.vit_dev_free.restype, L.vit_dev_free.argtypes = None, [vp]
+        L.vit_dev_sync.restype, L.vit_dev_sync.argtypes = C.c_int, []
+        L.vit_dev_count.restype, L.vit_dev_count.argtypes = C.c_int, []
         L.vit_synth_device.restype = C.c_int
         L.vit_synth_device.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, vp, vp, vp]
         _lib = L
@@ -93,6 +99,13 @@ def synth_device(input_type, n_bits, packed_ptr, bits_ptr=None, seed=1, amp=0, s
     source/encoder/noise/packer chain.  packed_ptr must hold whole 32-bit packs."""
     _check(lib().vit_synth_device(int(input_type), int(n_bits), int(seed), int(amp), float(sigma), int(bool(zero)),
                                   packed_ptr, bits_ptr, stream))
+
+
+def count_errors_device(options, out_ptr, bits_ptr, message_len, stream=0):
+    """Bit errors counted on the device (vit_count_errors_device): out bit j vs message bit j+26."""
+    n = C.c_ulonglong(0)
+    _check(lib().vit_count_errors_device(int(options), out_ptr, bits_ptr, int(message_len), C.byref(n), stream))
+    return int(n.value)
 
 
 class ViterbiCUDA:

@@ -76,11 +76,6 @@ constexpr bool inset0(int p, int qb) { return qb == mod6(p + 4) || qb == mod6(p 
 constexpr bool inset1(int p, int qb) { return qb == mod6(p + 3) || qb == mod6(p + 2) || qb == mod6(p); }
 
 // lane bit k <-> q bit 2k ; register/half bit k <-> q bit 2k+1
-constexpr int lane_mask(int which, int p) {
-    int m = 0;
-    for (int k = 0; k < 3; k++) m |= ((which ? inset1(p, 2 * k) : inset0(p, 2 * k)) ? 1 : 0) << k;
-    return m;
-}
 constexpr int reg_mask(int which, int p) {
     int m = 0;
     for (int k = 0; k < 3; k++) m |= ((which ? inset1(p, 2 * k + 1) : inset0(p, 2 * k + 1)) ? 1 : 0) << k;
@@ -220,8 +215,6 @@ template <int IN> struct Core<MET_B16, IN> {
     static constexpr uint32_t K2 = (uint32_t)(2 * b16_offset<IN>()) * 0x10001u;
     // all metric adds are `x*one + y` = IMAD on the FMA pipe; the ALU pipe is left to VIMNMX/SEL
     static VIT_HD uint32_t plus(uint32_t pm, uint32_t w, uint32_t one) { return pm * one + w; }
-    // operand of the opposite branch: (c - b) per half = K2 - w, no borrow because w <= K2 per half
-    static VIT_HD uint32_t neg(uint32_t w, uint32_t one) { return w * (0u - one) + K2; }
     // Add-compare-select of one packed register = two states.  part/own are the two candidates; the
     // partner wins ties (reference int16 core, viterbiACS.cuh:112-119,215-220: __vibmax_s16x2(partner - bm,
     // own + bm) -> pred = (a >= b)).  PTX max.s16x2 + setp.eq on the halves is what __vibmax_s16x2 expands to and
@@ -304,7 +297,6 @@ template <int IN> struct Core<MET_F16, IN> {
     static VIT_D __half2 h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
     static VIT_D uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
     static VIT_D uint32_t plus(uint32_t pm, uint32_t w, uint32_t) { return u32(__hadd2(h2(pm), h2(w))); }
-    static VIT_D uint32_t neg(uint32_t w, uint32_t) { return u32(__hneg2(h2(w))); }   // folds into HADD2's -operand
     // own wins ties (reference half2 core, viterbiACS.cuh:146-157,249-256: __hlt2_mask(own, partner)):
     // partner chosen iff partner > own.  HMNMX2 + HSETP2 (two predicates), then SEL or predicated IMAD.
     static VIT_D uint32_t acs_sel(uint32_t part, uint32_t own, uint32_t keep_lo, uint32_t src_lo, uint32_t keep_hi,
@@ -368,7 +360,6 @@ template <int IN> struct Core<MET_F16, IN> {
 template <int IN> struct Core<MET_B32, IN> {
     static constexpr bool PACKED = false;
     static VIT_HD uint32_t plus(uint32_t pm, uint32_t w, uint32_t one) { return pm * one + w; }      // IMAD
-    static VIT_HD uint32_t neg(uint32_t w, uint32_t one) { return w * (0u - one); }
     // partner wins ties except where the reference's phase-0 rule makes the odd predecessor win
     // (viterbiACS.cuh:136-142: both selfPM compares are "odd-candidate >= even-candidate").
     // One state per register: ISETP, metric select on the ALU pipe, survivor select on either pipe.

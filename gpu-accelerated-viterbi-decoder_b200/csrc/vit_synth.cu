@@ -83,6 +83,24 @@ __global__ void synth_kernel(SynthParams p, uint32_t* __restrict__ packed, uint8
     }
 }
 
+// decoded bit j (MSB-first inside its pack) vs message bit j + 26 (reference main.cpp:153-169)
+template <int BPP>
+__global__ void count_errors_kernel(const void* __restrict__ out, const uint8_t* __restrict__ bits, unsigned long long n_packs,
+                                    unsigned long long* __restrict__ total) {
+    unsigned long long errs = 0;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_packs;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t word = BPP == 16 ? static_cast<const uint16_t*>(out)[w] : static_cast<const uint32_t*>(out)[w];
+        uint32_t gen = 0;
+        const uint8_t* b = bits + w * BPP + 26;
+#pragma unroll 8
+        for (int k = 0; k < BPP; k++) gen = (gen << 1) | (b[k] & 1u);
+        errs += __popc(word ^ gen);
+    }
+    for (int d = 16; d > 0; d >>= 1) errs += __shfl_down_sync(0xffffffffu, errs, d);
+    if ((threadIdx.x & 31) == 0 && errs) atomicAdd(total, errs);
+}
+
 }  // namespace
 
 extern "C" {
@@ -110,6 +128,34 @@ int vit_synth_device(int input_type, size_t n_bits, unsigned seed, int amp, doub
         p, static_cast<uint32_t*>(packed_d), static_cast<uint8_t*>(bits_d), n_words);
     return cudaGetLastError() == cudaSuccess ? VIT_OK : VIT_ERR_CUDA;
 }
+
+// Bit errors of a decoded stream against the message bits (one byte per bit, e.g. from vit_synth_device),
+// counted on the device: errors = #{ j < messageLen : out bit j != bits[j + 26] }.  Synchronous.
+int vit_count_errors_device(int options, const void* out_d, const void* bits_d, size_t messageLen,
+                            unsigned long long* errors, void* cuda_stream) {
+    if (!out_d || !bits_d || !errors) return VIT_ERR_ARG;
+    const int bpp = ((options >> 8) & 0xf) == 1 ? 16 : 32;
+    unsigned long long* acc = nullptr;
+    if (cudaMalloc(&acc, sizeof *acc) != cudaSuccess) return VIT_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaMemsetAsync(acc, 0, sizeof *acc, st);
+    const unsigned long long n_packs = messageLen / bpp;
+    if (n_packs) {
+        const unsigned blocks = (unsigned)((n_packs + 255) / 256 < 148 * 16 ? (n_packs + 255) / 256 : 148 * 16);
+        if (bpp == 16) count_errors_kernel<16><<<blocks, 256, 0, st>>>(out_d, static_cast<const uint8_t*>(bits_d), n_packs, acc);
+        else count_errors_kernel<32><<<blocks, 256, 0, st>>>(out_d, static_cast<const uint8_t*>(bits_d), n_packs, acc);
+    }
+    cudaError_t e = cudaMemcpyAsync(errors, acc, sizeof *acc, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(acc);
+    return e == cudaSuccess ? VIT_OK : VIT_ERR_CUDA;
+}
+
+// plain device-memory helpers so that host-only callers (no CUDA headers) can use the device-resident entry points
+int vit_dev_alloc(void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes ? bytes : 1) == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
+void vit_dev_free(void* ptr) { if (ptr) cudaFree(ptr); }
+int vit_dev_sync(void) { return cudaDeviceSynchronize() == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
+int vit_dev_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 
 #pragma GCC visibility pop
 }

@@ -25,6 +25,7 @@ struct Args {
     int reps = 1;
     int streams = 1;
     int gpus = 1;
+    bool deviceSource = false;      // generate, decode and count errors on the device (no host pipeline)
 };
 
 static void usage(const char* prog) {
@@ -42,6 +43,8 @@ static void usage(const char* prog) {
               << "      --reps <integer>     Timed decoder runs (best kernel time is reported).\n"
               << "      --streams <integer>  Independent copies of the stream to decode (sharded over --gpus).\n"
               << "      --gpus <integer>     Number of GPUs (one decoder and one host thread per GPU).\n"
+              << "      --device-source      Generate the channel, decode and count bit errors on the device\n"
+              << "                           (counter-based source; needed for multi-Gbit -n, e.g. -n 4000000000 -i f).\n"
               << "  -h, --help               Display this help message.\n";
 }
 
@@ -79,6 +82,7 @@ static Args parseArg(int argc, char* argv[]) {
             a.options = (a.options & ~COMP_MASK) | lookup(f, value(), {{"REG", REG}, {"reg", REG}, {"DPX", DPX}, {"dpx", DPX}});
         else if (f == "-v" || f == "--verbose") a.verbose = true;
         else if (f == "--prbs") a.prbs = true;
+        else if (f == "--device-source") a.deviceSource = true;
         else if (f == "--seed") a.seed = number([](const std::string& s) { return std::stol(s); });
         else if (f == "--reps") a.reps = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
         else if (f == "--streams") a.streams = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
@@ -155,11 +159,45 @@ Outcome runPipeline(const Args& a) {
     return out;
 }
 
+// Device-resident variant of runPipeline: vit_synth_device -> ViterbiCUDA::runDevice -> vit_count_errors_device.
+// Same channel model shape as the host chain (BPSK +- amp, additive noise with sd = 10^(-snr/5) * amp, the
+// reference's saturating quantiser and packing) but counter based, so nothing of size n ever lives on the host.
+template <int options>
+Outcome runDevicePipeline(const Args& a) {
+    using Dec = ViterbiCUDA<options>;
+    Dec dec;
+    const size_t per = Dec::encDataPerPack;
+    const size_t inputNum = 2 * a.messageLen;
+    const size_t inBytes = (dec.getInputSize(inputNum) + 4 * per + 255) / 256 * 256;
+    const size_t outBytes = dec.getOutputSize(inputNum);
+    void *in_d = nullptr, *bits_d = nullptr, *out_d = nullptr;
+    VIT_HANDLE_ERROR(vit_dev_alloc(&in_d, inBytes));
+    VIT_HANDLE_ERROR(vit_dev_alloc(&bits_d, a.messageLen + 64));
+    VIT_HANDLE_ERROR(vit_dev_alloc(&out_d, outBytes + 256));
+    const unsigned seed = a.seed < 0 ? std::random_device{}() : static_cast<unsigned>(a.seed);
+    const double sigma = std::pow(10.0, -a.snr / 5.0);
+    VIT_HANDLE_ERROR(vit_synth_device(Dec::inputType >> CHANNEL_SHIFT, a.messageLen, seed, 0, sigma, 0, in_d, bits_d, nullptr));
+    VIT_HANDLE_ERROR(vit_dev_sync());
+    Outcome out;
+    out.best_ms = 1e30;
+    for (int r = 0; r < std::max(1, a.reps); ++r) {
+        float ms = 0.f;
+        dec.runDevice(in_d, out_d, inputNum, nullptr, &ms);
+        out.best_ms = std::min<double>(out.best_ms, ms);
+    }
+    out.decoded = dec.getMessageLen(inputNum);
+    unsigned long long errs = 0;
+    VIT_HANDLE_ERROR(vit_count_errors_device(options, out_d, bits_d, out.decoded, &errs, nullptr));
+    out.ben = errs;
+    vit_dev_free(in_d); vit_dev_free(bits_d); vit_dev_free(out_d);
+    return out;
+}
+
 // runtime options -> template instantiation (the reference: 60 nested-macro cases, main.cpp:79-104)
 template <int options>
 bool tryRun(const Args& a, Outcome& out) {
     if constexpr (OptionsValid<options>::value) {
-        if (a.options == options) { out = runPipeline<options>(a); return true; }
+        if (a.options == options) { out = a.deviceSource ? runDevicePipeline<options>(a) : runPipeline<options>(a); return true; }
     }
     return false;
 }

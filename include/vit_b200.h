@@ -96,6 +96,17 @@ int vit_set_segments(vit_handle* h, unsigned segments);
 int vit_synth_device(int input_type, size_t n_bits, unsigned seed, int amp, double sigma, int zero,
                      void* packed_d, void* bits_d, void* cuda_stream);
 
+/* Bit errors of a decoded stream counted on the device: #{ j < messageLen : out bit j != bits[j + 26] }
+ * (the reference's BER loop, src/main.cpp:153-169); bits_d holds one byte per message bit.  Synchronous. */
+int vit_count_errors_device(int options, const void* out_d, const void* bits_d, size_t messageLen,
+                            unsigned long long* errors, void* cuda_stream);
+
+/* device-memory helpers for host-only callers of the device-resident entry points (no CUDA headers needed) */
+int vit_dev_alloc(void** ptr, size_t bytes);
+void vit_dev_free(void* ptr);
+int vit_dev_sync(void);
+int vit_dev_count(void);
+
 const char* vit_last_error(void);
 
 #ifdef __cplusplus

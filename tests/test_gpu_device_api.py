@@ -215,3 +215,26 @@ def test_device_source_feeds_decoder(V, O):
         errs += int((db != d_b[26 + 32 * a:26 + 32 * b]).sum().item())
     assert errs == 0
     dec.close()
+
+
+def test_device_error_counter_and_harness_device_source(V, O):
+    import os
+    import re
+    import subprocess
+    import torch
+    from vit_testlib import PKG_DIR
+    # the device BER kernel agrees with the oracle's counter, for both pack widths
+    for opt in (0x011, 0x111):
+        bits, packed, N = O.make_channel_det(64 + 32 * 9000, O.SOFT4, seed=3, sigma=1.1)
+        out = O.decode(opt, packed, N)
+        M = O.message_len(opt, N)
+        d_o = torch.from_numpy(out.view(np.uint8).copy()).cuda()
+        d_b = torch.from_numpy(bits).cuda()
+        assert V.count_errors_device(opt, d_o.data_ptr(), d_b.data_ptr(), M) == O.count_errors(opt, out, M, bits) > 0
+    # the harness end to end on the device: 400 Mbit hard input never touches host memory
+    exe = os.path.join(PKG_DIR, "host", "main")
+    for args in (["-n", "400000000", "-i", "h", "-m", "b16", "-s", "5.5", "--device-source", "--seed", "7", "--reps", "2"],
+                 ["-n", "50000000", "-i", "f", "-m", "b32", "-o", "b16", "--device-source", "--seed", "8"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-500:]
+        assert int(re.search(r"BEN: (\d+)", out.stdout).group(1)) == 0, out.stdout[-400:]
