@@ -136,31 +136,41 @@ def count_errors_device(torch, out_u8, bits, M, bpp):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Samples are
+    stamped on arrival; mark()/unmark() bracket the timed region so that the summary can tell them apart from
+    the samples taken during the warm-up and kernel-timing loops (same kernels, same load)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_ms=5):
+        self.index, self.rows, self.proc, self.period_ms = index, [], None, period_ms
+        self.t_mark = self.t_unmark = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.15)               # let the first samples arrive before load starts
         except Exception:
             self.proc = None
         return self
 
+    def mark(self):
+        self.t_mark = time.perf_counter()
+
+    def unmark(self):
+        self.t_unmark = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.25)
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -168,16 +178,25 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        rows = [(t, r) for t, r in self.rows if len(r) >= 9 and num(r[1]) is not None]
+        inside = [(t, r) for t, r in rows if self.t_mark is not None and self.t_unmark is not None and self.t_mark <= t <= self.t_unmark + 0.01]
+        use = inside if inside else rows
+        sm = [num(r[1]) for _, r in use]
+        mx = [num(r[2]) for _, r in rows if num(r[2]) is not None]
+        pw = [num(r[3]) for _, r in use if num(r[3]) is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for _, r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons),
+                "samples_in_timed_region": len(inside), "samples_under_load": len(rows), "period_ms": self.period_ms}
 
 
 def measured_peaks():
@@ -248,7 +267,7 @@ def run_reference(args, options, n_bits, snr):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s4_b16_o32_32M", choices=sorted(WORKLOADS))
@@ -359,6 +378,15 @@ def main():
     launches0 = dec.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
+        for k in range(args.warmup):       # same kernels again: the sampler sees the load before the timed region too
+            step(k)
+        drain(args.warmup - 1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = dec.launch_count()
+        cs.mark()
         e0.record(st)
         for k in range(args.steps):
             step(k)
@@ -368,6 +396,7 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        cs.unmark()
         ms_total = e0.elapsed_time(e1)
         # kernel-only duration for the roofline: events bracketing the launch on the launch stream
         kms = []
