@@ -70,17 +70,51 @@ constexpr int LANES_PER_SEG = 8;
 constexpr int SEGS_PER_WARP = 4;
 constexpr int SUPER = 96;       // unroll period
 
-// symbol bit 0 (poly 0171) depends on q bits {p+4,p+3,p+2}, symbol bit 1 (poly 0133) on {p+3,p+2,p}
-// (indices mod 6); the butterfly bit (p+5) cancels because both polynomials tap bits 0 and 6.
-constexpr bool inset0(int p, int qb) { return qb == mod6(p + 4) || qb == mod6(p + 3) || qb == mod6(p + 2); }
-constexpr bool inset1(int p, int qb) { return qb == mod6(p + 3) || qb == mod6(p + 2) || qb == mod6(p); }
-
-// lane bit k <-> q bit 2k ; register/half bit k <-> q bit 2k+1
-constexpr int reg_mask(int which, int p) {
-    int m = 0;
-    for (int k = 0; k < 3; k++) m |= ((which ? inset1(p, 2 * k + 1) : inset0(p, 2 * k + 1)) ? 1 : 0) << k;
-    return m;
+// ------------------------------------------------------------------------------------------------
+// trellis state <-> (lane, register, half) map
+//
+// A position is a 6-bit vector v = [l0 l1 l2 | r0 r1 r2]: l = lane within the 8-lane group, r0 r1 = packed
+// register index, r2 = half of the packed register (int32 core: third register-index bit).  At every
+// stage the map position -> state is GF(2)-linear: state bit i = parity(v & f_i).  A trellis stage pairs
+// the two positions that differ only in state bit 0 (the butterfly) and writes the two new states back
+// in place, the new MSB u taking the value the position's old state bit 0 had, so the six functionals
+// just rotate (f_i <- f_{i+1}, f_5 <- f_0).  The map is chosen so that every butterfly joins two
+// registers (or the two halves of one register) of the SAME lane:
+//
+//   phase 0: butterfly along r1            (no data movement)
+//   phase 1: butterfly along r2            (half swap for the packed cores)
+//   phase 2..5: butterfly along r0, each preceded by a "half exchange": every lane sends its r0=1 registers
+//               (2 metric + 4 survivor registers) to lane ^ m, m = 1, 2, 4, 7, and keeps its r0=0 registers.
+//
+// The half exchange is the transvection v -> v + r0(v)*m of the position space: it substitutes
+// l -> l + r0*m in every functional, so that the functional about to become state bit 0 has a dual vector
+// without lane component.  The masks sum to zero (1^2^4^7), so the map has period 6 and everything below
+// is a compile-time function of the phase.  24 shuffles per 6 stages instead of the 36 of a map that
+// exchanges all 12 registers on the three lane-bit stages.
+// ------------------------------------------------------------------------------------------------
+constexpr int PB_R0 = 8, PB_R1 = 16, PB_R2 = 32;
+constexpr int par6(int v) { return ((v >> 0) ^ (v >> 1) ^ (v >> 2) ^ (v >> 3) ^ (v >> 4) ^ (v >> 5)) & 1; }
+constexpr int xmask_of(int p) { return p == 2 ? 1 : p == 3 ? 2 : p == 4 ? 4 : p == 5 ? 7 : 0; }   // exchange before stage p
+constexpr int cum_of(int p) { return p == 2 ? 1 : p == 3 ? 3 : p == 4 ? 7 : 0; }                   // sum of the masks so far
+constexpr int lprime(int j, int c) { return (1 << j) | (((c >> j) & 1) ? PB_R0 : 0); }              // l_j + r0*c_j
+// slot q = the functional whose butterfly is done at phase q, under accumulated exchange offset c
+constexpr int func_of_slot(int q, int c) {
+    return q == 0 ? PB_R1 : q == 1 ? PB_R2 : q == 2 ? (lprime(0, c) ^ lprime(1, c)) : q == 3 ? (lprime(1, c) ^ lprime(2, c))
+         : q == 4 ? lprime(2, c) : (PB_R0 ^ lprime(0, c));
 }
+// ... and its dual position vector (flips that state bit only)
+constexpr int dual_of_slot(int q, int c) {
+    return q == 0 ? PB_R1 : q == 1 ? PB_R2 : q == 2 ? ((1 ^ c) | PB_R0) : q == 3 ? ((3 ^ c) | PB_R0) : q == 4 ? ((7 ^ c) | PB_R0) : (c | PB_R0);
+}
+constexpr int f_before(int p, int i) { return func_of_slot(mod6(p + i), cum_of(p)); }      // state bit i entering stage p
+constexpr int f_after(int p, int i) { return func_of_slot(mod6(p + 1 + i), cum_of(p)); }   // state bit i leaving stage p
+
+// Own-branch symbol of a position entering stage p.  The encoder register is (u<<6)|S with u = S bit 0,
+// and both polynomials tap bits 0 and 6, so symbol bit 0 (poly 0171) = S3^S4^S5, symbol bit 1 (poly 0133) = S1^S3^S4.
+constexpr int sym_func(int which, int p) {
+    return which == 0 ? (f_before(p, 3) ^ f_before(p, 4) ^ f_before(p, 5)) : (f_before(p, 1) ^ f_before(p, 3) ^ f_before(p, 4));
+}
+constexpr int reg_mask(int which, int p) { return (sym_func(which, p) >> 3) & 7; }
 constexpr int par3(int v) { return ((v >> 0) ^ (v >> 1) ^ (v >> 2)) & 1; }
 
 // operand type of the own-branch metric for register index s8 at phase p:
@@ -89,23 +123,20 @@ constexpr int bm_type(int s8, int p) {
     int st0 = par3(s8 & reg_mask(0, p)), st1 = par3(s8 & reg_mask(1, p));
     return st0 == 0 ? (st1 == 0 ? 0 : 1) : (st1 == 0 ? 2 : 3);
 }
-// how the high half of a packed operand differs from the low half (does q5 tap poly0 / poly1)
-constexpr int half_variant(int p) { return (inset0(p, 5) ? 2 : 0) | (inset1(p, 5) ? 1 : 0); }
+// how the high half of a packed operand differs from the low half (does r2 enter symbol bit 0 / 1)
+constexpr int half_variant(int p) { return ((sym_func(0, p) & PB_R2) ? 2 : 0) | ((sym_func(1, p) & PB_R2) ? 1 : 0); }
 
 // stage kinds
-enum { KIND_HALF = 0, KIND_LANE = 1, KIND_REG = 2 };
-constexpr int beta(int p) { return mod6(p + 5); }  // butterfly q bit
+enum { KIND_HALF = 0, KIND_REG = 2 };
 template <int MET>
-constexpr int stage_kind(int p) {
-    return (beta(p) % 2 == 0) ? KIND_LANE : ((beta(p) == 5 && MET != MET_B32) ? KIND_HALF : KIND_REG);
-}
-constexpr int stage_bit(int p) { return beta(p) / 2; }  // lane bit or register bit index
+constexpr int stage_kind(int p) { return (p == 1 && MET != MET_B32) ? KIND_HALF : KIND_REG; }
+constexpr int stage_bit(int p) { return p == 0 ? 1 : p == 1 ? 2 : 0; }  // register-index bit of the butterfly
 
-// 6-bit survivor field (oldest message bit in the MSB) contributed by position bits at phase p
-constexpr int field_of_qbit(int qb, int p) { return 1 << (5 - mod6(qb - p)); }
+// 6-bit survivor field (oldest message bit = state bit 0 in the MSB) of register s8 leaving stage p; the
+// lane's part (lane_field_of) is XOR-ed in at run time
 constexpr int static_field(int s8, int p) {
     int f = 0;
-    for (int k = 0; k < 3; k++) if ((s8 >> k) & 1) f |= field_of_qbit(2 * k + 1, p);
+    for (int i = 0; i < 6; i++) if (par3(s8 & (f_after(p, i) >> 3))) f |= 1 << (5 - i);
     return f;
 }
 
@@ -430,38 +461,7 @@ VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
     constexpr int KIND = stage_kind<MET>(P);
     constexpr int BIT = stage_bit(P);
     const uint32_t one = ops.one;
-    if constexpr (KIND == KIND_LANE) {
-        constexpr int XM = 1 << BIT;
-        uint32_t ppm[LaneState<MET>::NPM], ppp[8];
-#pragma unroll
-        for (int r = 0; r < LaneState<MET>::NPM; r++) ppm[r] = shfl_xor(s.pm[r], XM);
-#pragma unroll
-        for (int k = 0; k < 8; k++) ppp[k] = shfl_xor(s.pp[k], XM);
-        if constexpr (C::PACKED) {
-#define VIT_LANE_PACKED(r)                                                                        \
-    {                                                                                             \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                                \
-        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                                  \
-        if constexpr ((r & 1) == 0)                                                               \
-            s.pm[r] = C::acs_sel(pc, oc, s.pp[r], ppp[r], s.pp[r + 4], ppp[r + 4], s.pp[r], s.pp[r + 4], false); \
-        else                                                                                      \
-            s.pm[r] = C::acs_mov(pc, oc, s.pp[r], ppp[r], s.pp[r + 4], ppp[r + 4], one, false);   \
-    }
-            VIT_LANE_PACKED(0) VIT_LANE_PACKED(1) VIT_LANE_PACKED(2) VIT_LANE_PACKED(3)
-#undef VIT_LANE_PACKED
-        } else {
-#define VIT_LANE_B32(r)                                                                           \
-    {                                                                                             \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                                \
-        uint32_t pc = cand<C, bm_type(r, P), true>(ppm[r], ops);                                  \
-        if constexpr ((r & 1) == 0) s.pm[r] = C::template acs1_sel<false>(pc, oc, s.pp[r], ppp[r], s.pp[r]); \
-        else s.pm[r] = C::template acs1_mov<false>(pc, oc, s.pp[r], ppp[r], one);                 \
-    }
-            VIT_LANE_B32(0) VIT_LANE_B32(1) VIT_LANE_B32(2) VIT_LANE_B32(3)
-            VIT_LANE_B32(4) VIT_LANE_B32(5) VIT_LANE_B32(6) VIT_LANE_B32(7)
-#undef VIT_LANE_B32
-        }
-    } else if constexpr (KIND == KIND_HALF) {
+    if constexpr (KIND == KIND_HALF) {
         // packed cores, phase 0: the two predecessors are the two halves of the same register
 #define VIT_HALF(r)                                                                               \
     {                                                                                             \
@@ -510,6 +510,20 @@ VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
     }
 }
 
+// pp | (lf ^ SF), or lf ^ SF when ASSIGN: one LOP3 with an immediate.  Written as PTX so that the loop-invariant
+// (lf ^ SF) is not hoisted into a register per (register, batch) pair -- that costs ~90 registers.
+template <bool ASSIGN, uint32_t SF>
+VIT_HD uint32_t or_xor(uint32_t pp, uint32_t lf) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    if (ASSIGN) asm("lop3.b32 %0, %1, %2, %3, 0x66;" : "=r"(r) : "r"(pp), "r"(lf), "n"(SF));
+    else asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(r) : "r"(pp), "r"(lf), "n"(SF));
+    return r;
+#else
+    return ASSIGN ? (lf ^ SF) : (pp | (lf ^ SF));
+#endif
+}
+
 // OR the survivors' newest message bits (== state index bits) into the register-exchange words.
 // NB bits (6 or 2) taken from the top of the 6-bit field, placed at bit SHIFT.
 template <int MET, int P, int SHIFT, int NB, bool ASSIGN>
@@ -518,33 +532,39 @@ VIT_HD void insert_field(LaneState<MET>& s, uint32_t lane_field) {
 #define VIT_INS(k)                                                                                \
     {                                                                                             \
         constexpr uint32_t sf = (uint32_t)(NB == 6 ? static_field(k, P) : (static_field(k, P) >> 4)) << SHIFT; \
-        s.pp[k] = ASSIGN ? (lf | sf) : (s.pp[k] | lf | sf);                                       \
+        s.pp[k] = or_xor<ASSIGN, sf>(s.pp[k], lf);                                                \
     }
     VIT_INS(0) VIT_INS(1) VIT_INS(2) VIT_INS(3) VIT_INS(4) VIT_INS(5) VIT_INS(6) VIT_INS(7)
 #undef VIT_INS
 }
 
-// position index (lane*8 + reg) of state `st` at phase p
-constexpr int pos_index_of_state(int st, int p) {
-    int q = ((st << p) | (st >> (6 - p))) & 63;  // rotl6
-    int l = ((q >> 0) & 1) | (((q >> 2) & 1) << 1) | (((q >> 4) & 1) << 2);
-    int r = ((q >> 1) & 1) | (((q >> 3) & 1) << 1) | (((q >> 5) & 1) << 2);
-    return l * 8 + r;
+// position index (lane*8 + reg) of the position that holds state `st` after the stage of phase p
+VIT_HD int pos_index_of_state(int st, int p) {
+    int v = 0;
+    for (int i = 0; i < 6; i++)
+        if ((st >> i) & 1) v ^= dual_of_slot(mod6(p + 1 + i), cum_of(p));
+    return (v & 7) * 8 + (v >> 3);
 }
 
+// the lane's part of the survivor field after the stage of phase p (XOR-ed with static_field)
 VIT_HD uint32_t lane_field_of(int l, int p) {
     uint32_t f = 0;
-    for (int k = 0; k < 3; k++)
-        if ((l >> k) & 1) f |= 1u << (5 - mod6(2 * k - p));
+    for (int i = 0; i < 6; i++)
+        if (par3(l & f_after(p, i) & 7)) f |= 1u << (5 - i);
     return f;
 }
+// the lane's part of the own-branch symbol entering stage p: operand class = 2*c0 + c1
 VIT_HD int lane_class_of(int l, int p) {
-    int c0 = 0, c1 = 0;
-    for (int k = 0; k < 3; k++) {
-        if (((l >> k) & 1) && inset0(p, 2 * k)) c0 ^= 1;
-        if (((l >> k) & 1) && inset1(p, 2 * k)) c1 ^= 1;
-    }
-    return c0 * 2 + c1;
+    return par3(l & sym_func(0, p) & 7) * 2 + par3(l & sym_func(1, p) & 7);
+}
+
+// Half exchange before the stages of phases 2..5: the r0=1 registers (metrics and survivors) swap with lane ^ XM.
+template <int MET, int XM>
+VIT_HD void exchange_half(LaneState<MET>& s) {
+#pragma unroll
+    for (int r = 1; r < LaneState<MET>::NPM; r += 2) s.pm[r] = shfl_xor(s.pm[r], XM);
+#pragma unroll
+    for (int k = 1; k < 8; k += 2) s.pp[k] = shfl_xor(s.pp[k], XM);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -772,6 +792,7 @@ VIT_HD void one_stage(WarpCtx<MET, IN, BPP>& c, const uint8_t* tbl) {
     // operands of the opposite branches cost a second LDS.64 instead of arithmetic
     const uint32_t* ent = reinterpret_cast<const uint32_t*>(tbl + row_off(S) + c.bm_off[P]);
     const uint32_t* entn = reinterpret_cast<const uint32_t*>(tbl + row_off(S) + c.bm_offn[P]);
+    if constexpr (xmask_of(P) != 0) exchange_half<MET, xmask_of(P)>(c.st);
 #if defined(__CUDA_ARCH__)
     const uint2 w = *reinterpret_cast<const uint2*>(ent);
     const uint2 n = *reinterpret_cast<const uint2*>(entn);
