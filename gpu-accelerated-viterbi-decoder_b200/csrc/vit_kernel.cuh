@@ -391,40 +391,72 @@ template <int IN> struct Core<MET_F16, IN> {
 template <int IN> struct Core<MET_B32, IN> {
     static constexpr bool PACKED = false;
     static VIT_HD uint32_t plus(uint32_t pm, uint32_t w, uint32_t one) { return pm * one + w; }      // IMAD
-    // partner wins ties except where the reference's phase-0 rule makes the odd predecessor win
-    // (viterbiACS.cuh:136-142: both selfPM compares are "odd-candidate >= even-candidate").
-    // One state per register: ISETP, metric select on the ALU pipe, survivor select on either pipe.
+    // One state per register.  partner wins ties except where the reference's phase-0 rule makes the odd
+    // predecessor win (viterbiACS.cuh:136-142: both selfPM compares are "odd-candidate >= even-candidate").
+    // The candidate that loses ties is never materialised: max(loser_metric + loser_operand, winner_candidate)
+    // is one fused VIADDMNMX, and the winner is chosen iff the result equals its candidate (ISETP.EQ) -- 4
+    // instructions per state (IMAD, VIADDMNMX, ISETP, select) instead of 5 (2 IMAD, ISETP, 2 SEL).
+    // acs1_sel writes the survivor to a new register (SEL, ALU pipe); acs1_mov moves it in place with a
+    // predicated IMAD (FMA pipe).
     template <bool OWN_WINS>
-    static VIT_HD uint32_t acs1_sel(uint32_t part, uint32_t own, uint32_t keep, uint32_t src, uint32_t& out) {
-        const int a = (int)part, b = (int)own;
+    static VIT_HD uint32_t acs1_sel(uint32_t pm_part, uint32_t op_part, uint32_t pm_own, uint32_t op_own, uint32_t keep,
+                                    uint32_t src, uint32_t& out, uint32_t one) {
+        uint32_t v;
+#if defined(__CUDA_ARCH__)
+        if (OWN_WINS)
+            asm("{.reg .pred p; .reg .s32 w, t; \n\t"
+                "mad.lo.s32 w, %2, %6, %3; \n\t"
+                "add.s32 t, %4, %5; \n\t"
+                "max.s32 %0, t, w; \n\t"
+                "setp.ne.s32 p, %0, w; \n\t"
+                "selp.b32 %1, %8, %7, p;} \n\t"
+                : "=r"(v), "=r"(out) : "r"(pm_own), "r"(op_own), "r"(pm_part), "r"(op_part), "r"(one), "r"(keep), "r"(src));
+        else
+            asm("{.reg .pred p; .reg .s32 w, t; \n\t"
+                "mad.lo.s32 w, %4, %6, %5; \n\t"
+                "add.s32 t, %2, %3; \n\t"
+                "max.s32 %0, t, w; \n\t"
+                "setp.eq.s32 p, %0, w; \n\t"
+                "selp.b32 %1, %8, %7, p;} \n\t"
+                : "=r"(v), "=r"(out) : "r"(pm_own), "r"(op_own), "r"(pm_part), "r"(op_part), "r"(one), "r"(keep), "r"(src));
+#else
+        const int a = (int)(pm_part + op_part), b = (int)(pm_own + op_own);
         const bool p = OWN_WINS ? (a > b) : (a >= b);
         out = p ? src : keep;
-        return (uint32_t)(p ? a : b);
+        v = (uint32_t)(p ? a : b);
+        (void)one;
+#endif
+        return v;
     }
     template <bool OWN_WINS>
-    static VIT_HD uint32_t acs1_mov(uint32_t part, uint32_t own, uint32_t& io, uint32_t src, uint32_t one) {
-#if defined(__CUDA_ARCH__)
+    static VIT_HD uint32_t acs1_mov(uint32_t pm_part, uint32_t op_part, uint32_t pm_own, uint32_t op_own, uint32_t& io,
+                                    uint32_t src, uint32_t one) {
         uint32_t v;
+#if defined(__CUDA_ARCH__)
         if (OWN_WINS)
-            asm("{.reg .pred p; \n\t"
-                "setp.gt.s32 p, %2, %3; \n\t"
-                "selp.b32 %0, %2, %3, p; \n\t"
-                "@p mad.lo.u32 %1, %4, %5, 0;} \n\t"
-                : "=r"(v), "+r"(io) : "r"(part), "r"(own), "r"(src), "r"(one));
+            asm("{.reg .pred p; .reg .s32 w, t; \n\t"
+                "mad.lo.s32 w, %2, %6, %3; \n\t"
+                "add.s32 t, %4, %5; \n\t"
+                "max.s32 %0, t, w; \n\t"
+                "setp.ne.s32 p, %0, w; \n\t"
+                "@p mad.lo.u32 %1, %7, %6, 0;} \n\t"
+                : "=r"(v), "+r"(io) : "r"(pm_own), "r"(op_own), "r"(pm_part), "r"(op_part), "r"(one), "r"(src));
         else
-            asm("{.reg .pred p; \n\t"
-                "setp.ge.s32 p, %2, %3; \n\t"
-                "selp.b32 %0, %2, %3, p; \n\t"
-                "@p mad.lo.u32 %1, %4, %5, 0;} \n\t"
-                : "=r"(v), "+r"(io) : "r"(part), "r"(own), "r"(src), "r"(one));
-        return v;
+            asm("{.reg .pred p; .reg .s32 w, t; \n\t"
+                "mad.lo.s32 w, %4, %6, %5; \n\t"
+                "add.s32 t, %2, %3; \n\t"
+                "max.s32 %0, t, w; \n\t"
+                "setp.eq.s32 p, %0, w; \n\t"
+                "@p mad.lo.u32 %1, %7, %6, 0;} \n\t"
+                : "=r"(v), "+r"(io) : "r"(pm_own), "r"(op_own), "r"(pm_part), "r"(op_part), "r"(one), "r"(src));
 #else
-        const int a = (int)part, b = (int)own;
+        const int a = (int)(pm_part + op_part), b = (int)(pm_own + op_own);
         const bool p = OWN_WINS ? (a > b) : (a >= b);
         if (p) io = src;
+        v = (uint32_t)(p ? a : b);
         (void)one;
-        return (uint32_t)(p ? a : b);
 #endif
+        return v;
     }
     static VIT_HD uint32_t vmin(uint32_t a, uint32_t b) { return (uint32_t)((int)a < (int)b ? (int)a : (int)b); }
     static VIT_HD uint32_t sub(uint32_t a, uint32_t m) { return a - m; }
@@ -446,6 +478,12 @@ template <int MET> struct LaneState {
 struct Operands { uint32_t x, y, nx, ny, one; };   // +X, +Y, -X, -Y in the core's operand encoding
 
 
+template <int TYPE, bool OPPOSITE>
+VIT_HD uint32_t opnd(const Operands& o) {
+    constexpr bool useY = (TYPE == 1 || TYPE == 2);
+    constexpr bool neg = ((TYPE == 2 || TYPE == 3) != OPPOSITE);
+    return neg ? (useY ? o.ny : o.nx) : (useY ? o.y : o.x);
+}
 template <class C, int TYPE, bool OPPOSITE>
 VIT_HD uint32_t cand(uint32_t metric, const Operands& o) {
     constexpr bool useY = (TYPE == 1 || TYPE == 2);
@@ -498,10 +536,10 @@ VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
         constexpr int rb = ra | (1 << BIT);                                                       \
         const uint32_t ea = s.pm[ra], eb = s.pm[rb];                                              \
         const uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb];                                            \
-        s.pm[ra] = C::template acs1_sel<false>(cand<C, bm_type(ra, P), true>(eb, ops),            \
-                                               cand<C, bm_type(ra, P), false>(ea, ops), pa0, pb0, s.pp[ra]); \
-        s.pm[rb] = C::template acs1_mov<ODD_WINS>(cand<C, bm_type(rb, P), true>(ea, ops),         \
-                                                  cand<C, bm_type(rb, P), false>(eb, ops), s.pp[rb], pa0, one); \
+        s.pm[ra] = C::template acs1_sel<false>(eb, opnd<bm_type(ra, P), true>(ops), ea, opnd<bm_type(ra, P), false>(ops), \
+                                               pa0, pb0, s.pp[ra], one);                          \
+        s.pm[rb] = C::template acs1_mov<ODD_WINS>(ea, opnd<bm_type(rb, P), true>(ops), eb, opnd<bm_type(rb, P), false>(ops), \
+                                                  s.pp[rb], pa0, one);                            \
     }
             VIT_REG_B32(0) VIT_REG_B32(1) VIT_REG_B32(2) VIT_REG_B32(3)
             VIT_REG_B32(4) VIT_REG_B32(5) VIT_REG_B32(6) VIT_REG_B32(7)
