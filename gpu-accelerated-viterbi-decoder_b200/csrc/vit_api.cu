@@ -13,7 +13,9 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 
 #include "../../include/vit_b200.h"
@@ -83,6 +85,12 @@ struct vit_handle {
     void* pin_in = nullptr; size_t pin_in_cap = 0;
     void* pin_out = nullptr; size_t pin_out_cap = 0;
     unsigned long long launches = 0;
+    // upload gates of the time-sliced host-buffer path (vit_run)
+    unsigned* gate_d = nullptr;          // [8] slice-arrived words + [1] error word
+    unsigned* epoch_h = nullptr;         // pinned: [0] the value the copy stream writes into a gate, [16] error word
+    unsigned* gate_err_d = nullptr;      // device address of epoch_h[16] (mapped): set by a warp that gave up waiting
+    unsigned epoch = 0;
+    cudaEvent_t ev_kdone = nullptr;
 };
 
 namespace {
@@ -106,9 +114,11 @@ int ensure_device_buffers(vit_handle* h, size_t in_bytes, size_t out_bytes) {
 }
 
 // decode segments [seg_first, seg_limit) of every stream; timing (optional) between caller-supplied events
+struct GatePlan { unsigned n = 0; unsigned super[8] = {}; };
+
 int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t nstreams,
                  size_t in_stride, size_t out_stride, cudaStream_t st, unsigned seg_first, unsigned seg_limit,
-                 cudaEvent_t e0, cudaEvent_t e1) {
+                 cudaEvent_t e0, cudaEvent_t e1, const GatePlan* gp = nullptr) {
     const int o = h->options;
     vitk::KParams kp;
     kp.in = static_cast<const uint8_t*>(in_d);
@@ -120,6 +130,12 @@ int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, 
     kp.seg_first = seg_first; kp.seg_limit = seg_limit;
     kp.nstreams = (unsigned)nstreams;
     kp.one = 1u;
+    kp.gate = h->gate_d; kp.gate_err = h->gate_err_d; kp.gate_epoch = h->epoch; kp.gate_n = 0;
+    for (int i = 0; i < 8; i++) kp.gate_super[i] = 0;
+    if (gp && h->gate_d) {
+        kp.gate_n = gp->n;
+        for (unsigned i = 0; i < gp->n; i++) kp.gate_super[i] = gp->super[i];
+    }
     dim3 grid((seg_limit - seg_first + vitk::SEGS_PER_WARP - 1) / vitk::SEGS_PER_WARP, (unsigned)nstreams, 1);
     if (e0) VIT_CUDA(cudaEventRecord(e0, st));
     VIT_CUDA(h->kernel->launch(kp, grid, st));
@@ -214,6 +230,11 @@ int vit_create(vit_handle** out, int options, int device, size_t prealloc_inputN
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_kdone, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->gate_d), 16 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(h->gate_d, 0, 16 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->epoch_h), 128, cudaHostAllocMapped);
+    if (e == cudaSuccess) { memset(h->epoch_h, 0, 128); e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->gate_err_d), h->epoch_h + 16, 0); }
     for (int i = 0; i < vit_handle::MAX_CHUNKS && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&h->chunk_stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
@@ -241,6 +262,9 @@ void vit_destroy(vit_handle* h) {
     if (h->pin_out) cudaFreeHost(h->pin_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_kdone) cudaEventDestroy(h->ev_kdone);
+    if (h->gate_d) cudaFree(h->gate_d);
+    if (h->epoch_h) cudaFreeHost(h->epoch_h);
     for (int i = 0; i < vit_handle::MAX_CHUNKS; i++) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_k0[i]) cudaEventDestroy(h->ev_k0[i]);
@@ -292,6 +316,90 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
         VIT_CUDA(cudaMemcpyAsync(out_h, h->out_d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
         VIT_CUDA(cudaStreamSynchronize(h->stream));
         return VIT_OK;
+    }
+    static const int run_mode = [] { const char* e = getenv("VIT_RUN_MODE"); return e ? atoi(e) : 0; }();
+    if (run_mode == 0 || run_mode == 3) {
+        // Time-sliced upload (pinned host input): ONE decode launch starts at once and every warp waits at
+        // "upload gates" for the next column block of its segments; the copy stream uploads block g of EVERY
+        // segment (two strided copies: the first P%W segments are one pack longer) and then opens gate g.  The
+        // decode therefore finishes one short block after the last byte has landed, instead of a whole
+        // per-segment chain (0.25-0.4 ms) after it as with segment-range chunks.
+        cudaPointerAttributes pa;
+        const bool pinned = cudaPointerGetAttributes(&pa, in_h) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const size_t P = vit_message_len(o, inputNum) / bpp, q = P / W, r = P % W;
+        const size_t b96 = in_type(o) == 0 ? 24 : in_type(o) == 1 ? 96 : in_type(o) == 2 ? 192 : in_type(o) == 3 ? 384 : 768;
+        const size_t Lmax = (q + (r ? 1 : 0)) * bpp, Tmax = 64 + 32 * ((Lmax + 31) / 32), nsuper = (Tmax + 95) / 96;
+        const size_t pack_bytes = bpp * b96 / 96;                 // channel bytes per decoded pack
+        if (pinned && q >= 1 && nsuper >= 16 && h->gate_d && h->gate_err_d && in_bytes >= (2u << 20)) {
+            GatePlan gp;
+            gp.n = 4;
+            gp.super[0] = 0; gp.super[1] = (unsigned)(nsuper / 2); gp.super[2] = (unsigned)(nsuper * 3 / 4); gp.super[3] = (unsigned)(nsuper * 7 / 8);
+            h->epoch++;
+            if (h->epoch == 0) h->epoch = 1;
+            *h->epoch_h = h->epoch;
+            timespec tb; clock_gettime(CLOCK_MONOTONIC, &tb);
+            const double t_begin = tb.tv_sec * 1e3 + tb.tv_nsec * 1e-6;
+            rc = launch_range(h, h->in_d, h->out_d, inputNum, 1, 0, 0, h->stream, 0, (unsigned)W, nullptr, h->ev_kdone, &gp);
+            if (rc) return rc;
+            VIT_CUDA(cudaMemcpyAsync(out_h, h->out_d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+            const char* src = static_cast<const char*>(in_h);
+            char* dst = static_cast<char*>(h->in_d);
+            const size_t pitch1 = (q + 1) * pack_bytes, pitch2 = q * pack_bytes;     // segment strides in bytes
+            const size_t grp2 = r * pitch1;                                          // first byte of segment r
+            const size_t body_end = P * pack_bytes;                                  // first byte after the last segment's own packs
+            // the last 64 stages of the stream (warm-up tail of the last segment) go with the first block
+            if (in_bytes > body_end)
+                VIT_CUDA(cudaMemcpyAsync(dst + body_end, src + body_end, in_bytes - body_end, cudaMemcpyHostToDevice, h->copy_stream));
+            for (unsigned g = 0; g < gp.n; g++) {
+                // columns [lo, hi) of every segment row: super-steps [super[g], super[g+1]) plus the read-ahead the
+                // kernel's 16-byte staging pieces take (<= 15 bytes before, <= 27 bytes after)
+                const size_t lo = g == 0 ? 0 : (size_t)gp.super[g] * b96 - 16;
+                const size_t hi = g + 1 == gp.n ? (size_t)-1 : (size_t)gp.super[g + 1] * b96 + 48;
+                if (r) {
+                    const size_t w1 = std::min(hi, pitch1);
+                    if (w1 > lo)
+                        VIT_CUDA(cudaMemcpy2DAsync(dst + lo, pitch1, src + lo, pitch1, w1 - lo, r, cudaMemcpyHostToDevice, h->copy_stream));
+                }
+                const size_t w2 = std::min(hi, pitch2);
+                if (w2 > lo)
+                    VIT_CUDA(cudaMemcpy2DAsync(dst + grp2 + lo, pitch2, src + grp2 + lo, pitch2, w2 - lo, W - r, cudaMemcpyHostToDevice, h->copy_stream));
+                VIT_CUDA(cudaMemcpyAsync(h->gate_d + g, h->epoch_h, sizeof(unsigned), cudaMemcpyHostToDevice, h->copy_stream));
+            }
+            static const bool dbg = getenv("VIT_RUN_DEBUG") != nullptr;
+            if (dbg) {
+                auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+                const double t_issued = now();
+                cudaStreamSynchronize(h->copy_stream);
+                const double t_copy = now();
+                cudaEventSynchronize(h->ev_kdone);
+                const double t_kernel = now();
+                cudaStreamSynchronize(h->stream);
+                const double t_all = now();
+                fprintf(stderr, "[vit_run gated] issue %.3f ms, upload done +%.3f, kernel done +%.3f, download done +%.3f\n",
+                        t_issued - t_begin, t_copy - t_begin, t_kernel - t_begin, t_all - t_begin);
+            }
+            VIT_CUDA(cudaStreamSynchronize(h->copy_stream));
+            VIT_CUDA(cudaStreamSynchronize(h->stream));
+            if (*static_cast<volatile unsigned*>(h->epoch_h + 16)) {
+                h->epoch_h[16] = 0;
+                return fail(VIT_ERR_CUDA, "decode kernel gave up waiting for the input upload");
+            }
+            return VIT_OK;
+        }
+    }
+    if (run_mode == 1) {
+        // experiment (VIT_RUN_MODE=1): the kernel reads the channel words straight from pinned host memory (zero copy)
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, in_h) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+            (reinterpret_cast<uintptr_t>(pa.devicePointer) & 15) == 0) {
+            rc = launch(h, pa.devicePointer, h->out_d, inputNum, 1, 0, 0, h->stream, nullptr);
+            if (rc) return rc;
+            VIT_CUDA(cudaMemcpyAsync(out_h, h->out_d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+            VIT_CUDA(cudaStreamSynchronize(h->stream));
+            return VIT_OK;
+        }
+        cudaGetLastError();
     }
     // No timing requested: overlap the three phases.  The stream is cut at segment boundaries into nch
     // chunks (segments are independent: chunk i needs the input bytes up to the end of its last segment's

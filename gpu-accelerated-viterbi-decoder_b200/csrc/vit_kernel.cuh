@@ -60,6 +60,14 @@ struct KParams {
     unsigned nstreams;
     unsigned one;                   // == 1, opaque to the compiler: `x*one + y` is emitted as IMAD so that
                                     // the metric adds run on the FMA pipe while VIMNMX/SEL own the ALU pipe
+    // Upload gates (vit_run with host buffers, time-sliced copy-in): the channel words arrive while the kernel
+    // runs, every segment's super-steps [gate_super[g], gate_super[g+1]) with copy slice g.  A warp may read
+    // super-step x only after gate[g] == gate_epoch for every g with gate_super[g] <= x.  gate_n == 0: no gating.
+    const unsigned* gate;
+    unsigned* gate_err;             // set to 1 by a warp that gave up waiting (upload never arrived)
+    unsigned gate_epoch;
+    unsigned gate_n;
+    unsigned gate_super[8];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -192,6 +200,22 @@ VIT_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memo
 template <int N> VIT_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 VIT_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 VIT_D uint32_t brev32(uint32_t v) { return __brev(v); }
+// wait until *flag == epoch (written by the host's copy stream after the slice's bytes); gives up after ~2 s
+VIT_D bool gate_spin(const unsigned* flag, unsigned epoch) {
+    unsigned long long t0 = 0;
+    for (unsigned it = 1;; it++) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) return true;
+        __nanosleep(it < 8 ? 200 : 1000);
+        if ((it & 255u) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) return false;
+        }
+    }
+}
 #else
 uint32_t emu_shfl_xor(uint32_t v, int m);
 uint32_t emu_shfl_idx(uint32_t v, int src);
@@ -222,6 +246,7 @@ inline uint32_t brev32(uint32_t v) {
     for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
     return r;
 }
+inline bool gate_spin(const unsigned* flag, unsigned epoch) { return *flag == epoch; }
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -867,6 +892,14 @@ VIT_HD bool slide(WarpCtx<MET, IN, BPP>& c, unsigned Tmax) {
     return c.t0 + 32 * (W + 1) >= Tmax;
 }
 
+// kp.gate_super[i] without dynamic indexing of the kernel parameters (that would copy them to local memory)
+VIT_HD unsigned gate_super_at(const KParams& kp, unsigned i) {
+    unsigned v = kp.gate_super[0];
+#pragma unroll
+    for (unsigned k = 1; k < 8; k++) v = (i == k) ? kp.gate_super[k] : v;
+    return v;
+}
+
 // Decode the 4 segments owned by warp `warp_id` of stream `stream`.
 template <int MET, int IN, int BPP>
 VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int lane, uint8_t* smem) {
@@ -920,6 +953,14 @@ VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int 
         }
     }
 
+    // upload gates passed so far (uniform across the warp)
+    unsigned gate_next = 0;
+#define VIT_GATE(x)                                                                               \
+    while (gate_next < kp.gate_n && (x) >= gate_super_at(kp, gate_next)) {                        \
+        if (!gate_spin(kp.gate + gate_next, kp.gate_epoch)) { *kp.gate_err = 1u; return; }        \
+        gate_next++;                                                                              \
+    }
+    VIT_GATE(0u)
     issue_raw_copy(c, 0);
 #pragma unroll 1
     for (unsigned sc = 0; sc < nsuper; sc++) {
@@ -929,13 +970,17 @@ VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int 
         syncwarp();
         build_table(c, skew);
         syncwarp();
-        if (sc + 1 < nsuper) issue_raw_copy(c, sc + 1);       // lands while the 96 stages below run
+        if (sc + 1 < nsuper) {
+            VIT_GATE(sc + 1)
+            issue_raw_copy(c, sc + 1);                         // lands while the 96 stages below run
+        }
         if constexpr (norm_period<MET, IN>() != 32) normalize<MET, IN>(c.st);
         if (slide<MET, IN, BPP, 0>(c, Tmax)) break;
         if (slide<MET, IN, BPP, 1>(c, Tmax)) break;
         if (slide<MET, IN, BPP, 2>(c, Tmax)) break;
         syncwarp();
     }
+#undef VIT_GATE
 }
 
 #if defined(__CUDACC__)

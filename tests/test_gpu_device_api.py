@@ -238,3 +238,36 @@ def test_device_error_counter_and_harness_device_source(V, O):
         out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-500:]
         assert int(re.search(r"BEN: (\d+)", out.stdout).group(1)) == 0, out.stdout[-400:]
+
+
+@pytest.mark.parametrize("opt,n", [
+    (0x011, 6400 * 32 * 60 + 64),            # s4, every segment the same length (P % W == 0)
+    (0x011, 6400 * 32 * 52 + 32 * 1234 + 64 + 5),   # ragged: the first 1234 segments are one pack longer
+    (0x000, 6400 * 32 * 330 + 32 * 77 + 64),  # hard input: 24 channel bytes per super-step, not 16-byte multiples
+    (0x112, 6400 * 16 * 101 + 16 * 3 + 64),   # 16-bit packs, odd pack count per segment
+    (0x004, 6400 * 32 * 50 + 64 + 32 * 6399), # fp32 input
+])
+def test_host_run_time_sliced_upload(V, O, opt, n):
+    """vit_run with PINNED host buffers takes the time-sliced upload path (one launch, upload gates inside the
+    kernel); its output must equal the device-resident decode of the same bytes and the golden model."""
+    import torch
+    bits, packed, N = O.make_channel_det(n, opt & 0xF, seed=77, sigma=0.7)
+    dec = V.ViterbiCUDA(opt, N)
+    in_bytes, out_bytes = dec.getInputSize(N), dec.getOutputSize(N)
+    assert in_bytes >= 2 << 20
+    h_in = torch.from_numpy(packed.view(np.uint8)[:in_bytes].copy()).pin_memory()
+    h_out = torch.zeros(out_bytes, dtype=torch.uint8).pin_memory()
+    launches = dec.launch_count()
+    for rep in range(3):
+        h_out.zero_()
+        dec.run(h_in.numpy(), N, output_h=h_out.numpy().view(dec.decPack_t))
+    assert dec.launch_count() - launches == 3          # one launch per run: the gated path, not the chunk pipeline
+    d_in = h_in.cuda()
+    d_out = torch.zeros(out_bytes + 256, dtype=torch.uint8, device="cuda")
+    dec.run_device(d_in.data_ptr(), d_out.data_ptr(), N)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out[:out_bytes].cpu(), h_out)
+    exp = O.decode(opt, packed, N)
+    got = h_out.numpy().view(dec.decPack_t)
+    assert np.array_equal(got, exp)
+    dec.close()
