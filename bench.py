@@ -136,21 +136,42 @@ def count_errors_device(torch, out_u8, bits, M, bpp):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Samples are
-    stamped on arrival; mark()/unmark() bracket the timed region so that the summary can tell them apart from
-    the samples taken during the warm-up and kernel-timing loops (same kernels, same load)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  A thread polls NVML
+    (pynvml, ~0.1 ms per query) every period_ms; if NVML is unavailable it falls back to `nvidia-smi -lms`.
+    mark()/unmark() bracket the timed region so that the summary can tell its samples from the ones taken during
+    the warm-up and kernel-timing loops (same kernels, same load)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_ms=5):
+    def __init__(self, index, period_ms=2):
         self.index, self.rows, self.proc, self.period_ms = index, [], None, period_ms
         self.t_mark = self.t_unmark = None
+        self.stop, self.t, self.nv, self.max_mhz, self.source = False, None, None, None, None
 
     def __enter__(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except ValueError:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv, self.source = pynvml, "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                          "--format=csv,noheader,nounits", "-lms", str(max(self.period_ms, 5))],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
             time.sleep(0.15)               # let the first samples arrive before load starts
@@ -164,11 +185,42 @@ class ClockSampler:
     def unmark(self):
         self.t_unmark = time.perf_counter()
 
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = ((getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4), "sw_power_cap"))
+        while not self.stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                flags = ["Active" if mask & b else "Not Active" for b, _ in bits]
+                self.rows.append((time.perf_counter(), [str(self.index), str(mhz), str(self.max_mhz), str(pw), hex(mask)] + flags))
+            except Exception:
+                pass
+            time.sleep(self.period_ms / 1000.0)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
+        self.stop = True
+        if self.nv is not None:
+            if self.t:
+                self.t.join(timeout=1)
+            try:
+                self.nv.nvmlShutdown()
+            except Exception:
+                pass
         if self.proc:
             time.sleep(0.05)
             self.proc.terminate()
@@ -181,10 +233,10 @@ class ClockSampler:
         def num(v):
             try:
                 return float(v)
-            except ValueError:
+            except (ValueError, TypeError):
                 return None
         rows = [(t, r) for t, r in self.rows if len(r) >= 9 and num(r[1]) is not None]
-        inside = [(t, r) for t, r in rows if self.t_mark is not None and self.t_unmark is not None and self.t_mark <= t <= self.t_unmark + 0.01]
+        inside = [(t, r) for t, r in rows if self.t_mark is not None and self.t_unmark is not None and self.t_mark <= t <= self.t_unmark + 0.002]
         use = inside if inside else rows
         sm = [num(r[1]) for _, r in use]
         mx = [num(r[2]) for _, r in rows if num(r[2]) is not None]
@@ -196,7 +248,8 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons),
-                "samples_in_timed_region": len(inside), "samples_under_load": len(rows), "period_ms": self.period_ms}
+                "samples_in_timed_region": len(inside), "samples_under_load": len(rows), "period_ms": self.period_ms,
+                "source": self.source}
 
 
 def measured_peaks():

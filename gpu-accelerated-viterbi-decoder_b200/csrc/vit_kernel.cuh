@@ -166,14 +166,17 @@ template <int IN> constexpr int b16_offset() { return IN == IN_HARD ? 1 : IN == 
 // 6 apart, store to 8 different 16-byte bank columns (conflict-free STS.128).
 constexpr int BM_ROW = SEGS_PER_WARP * 4 * 8;            // 128
 constexpr int BM_JBLOCK = 6 * BM_ROW + 16;               // 784
-constexpr int row_off(int s) { return (s / 6) * BM_JBLOCK + (s % 6) * BM_ROW; }   // stage within super-step -> table row
+// stage within the super-step -> table row.  TBL = stages the table holds: 96 (built once per super-step) or 32
+// (rebuilt before every slide: 1/3 of the shared memory, twice the resident warps, for multi-stream launches)
+template <int TBL>
+constexpr int row_off(int s) { return ((s % TBL) / 6) * BM_JBLOCK + ((s % TBL) % 6) * BM_ROW; }
 // Ring: per (slot, segment) 64 words + 16 B pad; lane l stores its 8 words at l*32 + (l>>2)*16 so that
 // the two STS.128 of a flush are conflict-free as well.
 constexpr int RING_SEG = 64 * 4 + 16;                    // 272
 constexpr int ring_word_of(int l, int r) { return l * 8 + (l >> 2) * 4 + r; }
 
-template <int IN> struct Smem {
-    static constexpr int BM_BYTES = (SUPER / 6) * BM_JBLOCK;                       // 12544
+template <int IN, int TBL = 96> struct Smem {
+    static constexpr int BM_BYTES = ((TBL + 5) / 6) * BM_JBLOCK;                   // 12544 | 4704
     static constexpr int RAW_SEG = raw_pieces<IN>() * 16;
     static constexpr int RAW_BYTES = SEGS_PER_WARP * RAW_SEG;      // single buffer: consumed whole by the table build
     static constexpr int RING_BYTES = 3 * SEGS_PER_WARP * RING_SEG;                // 3264
@@ -703,7 +706,7 @@ VIT_HD void build_step(const uint8_t* raw, int rel_stage, uint32_t* entry /* 8 w
 // ------------------------------------------------------------------------------------------------
 // the warp body
 // ------------------------------------------------------------------------------------------------
-template <int MET, int IN, int BPP>
+template <int MET, int IN, int BPP, int TBL>
 struct WarpCtx {
     LaneState<MET> st;
     uint8_t* smem;
@@ -722,9 +725,9 @@ struct WarpCtx {
     unsigned t0;                    // absolute stage index of the current superchunk's stage 0
 };
 
-template <int MET, int IN, int BPP>
-VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP>& c, unsigned super_idx) {
-    using S = Smem<IN>;
+template <int MET, int IN, int BPP, int TBL>
+VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP, TBL>& c, unsigned super_idx) {
+    using S = Smem<IN, TBL>;
     constexpr int B96 = InTraits<IN>::B96;
     unsigned long long b0 = c.seg_byte0 + (unsigned long long)super_idx * B96;
     unsigned long long al = b0 & ~15ull;
@@ -742,15 +745,7 @@ VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP>& c, unsigned super_idx) {
     cp_async_commit();
 }
 
-// lane l of the group builds the rows of stages P + 6*(l + 8*round): j-block l + 8*round, row P
-template <int MET, int IN, int BPP, int P>
-VIT_HD void build_phase(WarpCtx<MET, IN, BPP>& c, int round, unsigned skew) {
-    using S = Smem<IN>;
-    const uint8_t* raw = c.smem + S::OFF_RAW + c.g * S::RAW_SEG + skew;
-    const int j = c.l + 8 * round;
-    uint32_t e[8];
-    build_step<MET, IN, P>(raw, P + 6 * j, e);
-    uint32_t* row = reinterpret_cast<uint32_t*>(c.smem + S::OFF_BM + j * BM_JBLOCK + P * BM_ROW + c.g * 32);
+VIT_HD void store_row(uint32_t* row, const uint32_t (&e)[8]) {
 #if defined(__CUDA_ARCH__)
     reinterpret_cast<uint4*>(row)[0] = make_uint4(e[0], e[1], e[2], e[3]);
     reinterpret_cast<uint4*>(row)[1] = make_uint4(e[4], e[5], e[6], e[7]);
@@ -759,17 +754,54 @@ VIT_HD void build_phase(WarpCtx<MET, IN, BPP>& c, int round, unsigned skew) {
 #endif
 }
 
-template <int MET, int IN, int BPP>
-VIT_HD void build_table(WarpCtx<MET, IN, BPP>& c, unsigned skew) {
+// lane l of the group builds the rows of stages P + 6*(l + 8*round): j-block l + 8*round, row P
+template <int MET, int IN, int BPP, int TBL, int P>
+VIT_HD void build_phase(WarpCtx<MET, IN, BPP, TBL>& c, int round, unsigned skew) {
+    using S = Smem<IN, TBL>;
+    const uint8_t* raw = c.smem + S::OFF_RAW + c.g * S::RAW_SEG + skew;
+    const int j = c.l + 8 * round;
+    uint32_t e[8];
+    build_step<MET, IN, P>(raw, P + 6 * j, e);
+    uint32_t* row = reinterpret_cast<uint32_t*>(c.smem + S::OFF_BM + j * BM_JBLOCK + P * BM_ROW + c.g * 32);
+    store_row(row, e);
+}
+
+template <int MET, int IN, int BPP, int TBL>
+VIT_HD void build_table(WarpCtx<MET, IN, BPP, TBL>& c, unsigned skew) {
 #pragma unroll 1
     for (int round = 0; round < 2; round++) {
-        build_phase<MET, IN, BPP, 0>(c, round, skew);
-        build_phase<MET, IN, BPP, 1>(c, round, skew);
-        build_phase<MET, IN, BPP, 2>(c, round, skew);
-        build_phase<MET, IN, BPP, 3>(c, round, skew);
-        build_phase<MET, IN, BPP, 4>(c, round, skew);
-        build_phase<MET, IN, BPP, 5>(c, round, skew);
+        build_phase<MET, IN, BPP, TBL, 0>(c, round, skew);
+        build_phase<MET, IN, BPP, TBL, 1>(c, round, skew);
+        build_phase<MET, IN, BPP, TBL, 2>(c, round, skew);
+        build_phase<MET, IN, BPP, TBL, 3>(c, round, skew);
+        build_phase<MET, IN, BPP, TBL, 4>(c, round, skew);
+        build_phase<MET, IN, BPP, TBL, 5>(c, round, skew);
     }
+}
+
+// TBL == 32: the rows of slide W (stages 32W .. 32W+31) are built just before it runs.  Lane l builds stage
+// 32W + 6l + r in step r (phase (32W + r) % 6 is static per step), i.e. j-block l, row r; lanes 6,7 idle.
+template <int MET, int IN, int BPP, int TBL, int W>
+VIT_HD void build_slide(WarpCtx<MET, IN, BPP, TBL>& c, unsigned skew) {
+    using S = Smem<IN, TBL>;
+    const uint8_t* raw = c.smem + S::OFF_RAW + c.g * S::RAW_SEG + skew;
+    int l = c.l;
+#if defined(__CUDA_ARCH__)
+    // opaque copy of the lane index: the per-row shift amounts and offsets derived from it are loop invariant, and
+    // hoisting all 18 sets of them out of the super-step loop costs ~50 registers (occupancy is the point of TBL=32)
+    asm volatile("" : "+r"(l));
+#endif
+    uint8_t* blk = c.smem + S::OFF_BM + l * BM_JBLOCK + c.g * 32;
+#define VIT_BUILD_ROW(r)                                                                          \
+    if (6 * l + r < 32) {                                                                         \
+        uint32_t e[8];                                                                            \
+        build_step<MET, IN, (32 * W + r) % 6>(raw, 32 * W + 6 * l + r, e);                        \
+        uint32_t* row = reinterpret_cast<uint32_t*>(blk + r * BM_ROW);                            \
+        store_row(row, e);                                                                        \
+    }
+    VIT_BUILD_ROW(0) VIT_BUILD_ROW(1) VIT_BUILD_ROW(2) VIT_BUILD_ROW(3) VIT_BUILD_ROW(4) VIT_BUILD_ROW(5)
+#undef VIT_BUILD_ROW
+    syncwarp();
 }
 
 // subtract the segment-wide minimum metric (a common offset never changes a decision; the
@@ -796,9 +828,9 @@ template <int MET, int IN> constexpr int norm_period() {
 // End of a 32-stage slide (superchunk stage S = 32*SLOT + 31, phase P = S % 6): flush the
 // register-exchange words to ring slot SLOT, trace back from state 0, emit 32 decoded bits, start
 // the next survivor word.
-template <int MET, int IN, int BPP, int SLOT>
-VIT_HD void slide_end(WarpCtx<MET, IN, BPP>& c) {
-    using SM = Smem<IN>;
+template <int MET, int IN, int BPP, int TBL, int SLOT>
+VIT_HD void slide_end(WarpCtx<MET, IN, BPP, TBL>& c) {
+    using SM = Smem<IN, TBL>;
     constexpr int S = 32 * SLOT + 31;
     constexpr int P = S % 6;                      // 1, 3, 5 for slots 0, 1, 2
     uint8_t* ringb = c.smem + SM::OFF_RING;
@@ -848,13 +880,13 @@ VIT_HD void insert_batch(LaneState<MET>& st, uint32_t lane_field, int i) {
 }
 
 // stage S of the super-step; tbl = table base advanced by the loop iteration (i * BM_JBLOCK)
-template <int MET, int IN, int BPP, int S>
-VIT_HD void one_stage(WarpCtx<MET, IN, BPP>& c, const uint8_t* tbl) {
+template <int MET, int IN, int BPP, int TBL, int S>
+VIT_HD void one_stage(WarpCtx<MET, IN, BPP, TBL>& c, const uint8_t* tbl) {
     constexpr int P = S % 6;
     // class c holds (X, Y) in the core's operand encoding; class 3-c holds exactly (-X, -Y), so the
     // operands of the opposite branches cost a second LDS.64 instead of arithmetic
-    const uint32_t* ent = reinterpret_cast<const uint32_t*>(tbl + row_off(S) + c.bm_off[P]);
-    const uint32_t* entn = reinterpret_cast<const uint32_t*>(tbl + row_off(S) + c.bm_offn[P]);
+    const uint32_t* ent = reinterpret_cast<const uint32_t*>(tbl + row_off<TBL>(S) + c.bm_off[P]);
+    const uint32_t* entn = reinterpret_cast<const uint32_t*>(tbl + row_off<TBL>(S) + c.bm_offn[P]);
     if constexpr (xmask_of(P) != 0) exchange_half<MET, xmask_of(P)>(c.st);
 #if defined(__CUDA_ARCH__)
     const uint2 w = *reinterpret_cast<const uint2*>(ent);
@@ -870,25 +902,25 @@ VIT_HD void one_stage(WarpCtx<MET, IN, BPP>& c, const uint8_t* tbl) {
 //   2 stages ; flush + traceback + emit     (stage 32W+31)
 // One loop branch and one batch dispatch per 6 stages; everything else is straight-line.
 // Returns true when the segment group has emitted its last word.
-template <int MET, int IN, int BPP, int W>
-VIT_HD bool slide(WarpCtx<MET, IN, BPP>& c, unsigned Tmax) {
-    using SM = Smem<IN>;
+template <int MET, int IN, int BPP, int TBL, int W>
+VIT_HD bool slide(WarpCtx<MET, IN, BPP, TBL>& c, unsigned Tmax) {
+    using SM = Smem<IN, TBL>;
     constexpr int S0 = 32 * W;
     constexpr int PB = (S0 + 5) % 6;              // phase of the batch stages: 5, 1, 3
     const uint8_t* tbl = c.smem + SM::OFF_BM;
 #pragma unroll 1
     for (int i = 0; i < 5; i++, tbl += BM_JBLOCK) {
-        one_stage<MET, IN, BPP, S0 + 0>(c, tbl);
-        one_stage<MET, IN, BPP, S0 + 1>(c, tbl);
-        one_stage<MET, IN, BPP, S0 + 2>(c, tbl);
-        one_stage<MET, IN, BPP, S0 + 3>(c, tbl);
-        one_stage<MET, IN, BPP, S0 + 4>(c, tbl);
-        one_stage<MET, IN, BPP, S0 + 5>(c, tbl);
+        one_stage<MET, IN, BPP, TBL, S0 + 0>(c, tbl);
+        one_stage<MET, IN, BPP, TBL, S0 + 1>(c, tbl);
+        one_stage<MET, IN, BPP, TBL, S0 + 2>(c, tbl);
+        one_stage<MET, IN, BPP, TBL, S0 + 3>(c, tbl);
+        one_stage<MET, IN, BPP, TBL, S0 + 4>(c, tbl);
+        one_stage<MET, IN, BPP, TBL, S0 + 5>(c, tbl);
         insert_batch<MET, PB>(c.st, c.lane_field[PB / 2], i);
     }
-    one_stage<MET, IN, BPP, S0 + 30>(c, c.smem + SM::OFF_BM);
-    one_stage<MET, IN, BPP, S0 + 31>(c, c.smem + SM::OFF_BM);
-    slide_end<MET, IN, BPP, W>(c);
+    one_stage<MET, IN, BPP, TBL, S0 + 30>(c, c.smem + SM::OFF_BM);
+    one_stage<MET, IN, BPP, TBL, S0 + 31>(c, c.smem + SM::OFF_BM);
+    slide_end<MET, IN, BPP, TBL, W>(c);
     return c.t0 + 32 * (W + 1) >= Tmax;
 }
 
@@ -901,10 +933,10 @@ VIT_HD unsigned gate_super_at(const KParams& kp, unsigned i) {
 }
 
 // Decode the 4 segments owned by warp `warp_id` of stream `stream`.
-template <int MET, int IN, int BPP>
+template <int MET, int IN, int BPP, int TBL = 96>
 VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int lane, uint8_t* smem) {
-    using SM = Smem<IN>;
-    WarpCtx<MET, IN, BPP> c;
+    using SM = Smem<IN, TBL>;
+    WarpCtx<MET, IN, BPP, TBL> c;
     c.smem = smem; c.lane = lane; c.g = lane >> 3; c.l = lane & 7;
     c.one = kp.one;
 
@@ -968,26 +1000,39 @@ VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int 
         const unsigned skew = (unsigned)((c.seg_byte0 + (unsigned long long)sc * InTraits<IN>::B96) & 15ull);
         cp_async_wait<0>();
         syncwarp();
-        build_table(c, skew);
-        syncwarp();
-        if (sc + 1 < nsuper) {
-            VIT_GATE(sc + 1)
-            issue_raw_copy(c, sc + 1);                         // lands while the 96 stages below run
+        // the raw staging buffer is single: the next super-step's words are requested as soon as the last table
+        // build of this one has consumed it, and land while the remaining stages run
+#define VIT_PREFETCH                                                                              \
+    if (sc + 1 < nsuper) {                                                                        \
+        VIT_GATE(sc + 1)                                                                          \
+        issue_raw_copy(c, sc + 1);                                                                \
+    }
+        if constexpr (TBL == 96) {
+            build_table(c, skew);
+            syncwarp();
+            VIT_PREFETCH
         }
         if constexpr (norm_period<MET, IN>() != 32) normalize<MET, IN>(c.st);
-        if (slide<MET, IN, BPP, 0>(c, Tmax)) break;
-        if (slide<MET, IN, BPP, 1>(c, Tmax)) break;
-        if (slide<MET, IN, BPP, 2>(c, Tmax)) break;
+        if constexpr (TBL == 32) build_slide<MET, IN, BPP, TBL, 0>(c, skew);
+        if (slide<MET, IN, BPP, TBL, 0>(c, Tmax)) break;
+        if constexpr (TBL == 32) build_slide<MET, IN, BPP, TBL, 1>(c, skew);
+        if (slide<MET, IN, BPP, TBL, 1>(c, Tmax)) break;
+        if constexpr (TBL == 32) {
+            build_slide<MET, IN, BPP, TBL, 2>(c, skew);
+            VIT_PREFETCH
+        }
+        if (slide<MET, IN, BPP, TBL, 2>(c, Tmax)) break;
         syncwarp();
     }
+#undef VIT_PREFETCH
 #undef VIT_GATE
 }
 
 #if defined(__CUDACC__)
-template <int MET, int IN, int BPP>
+template <int MET, int IN, int BPP, int TBL>
 __global__ void __launch_bounds__(32) vit_decode_kernel(const KParams kp) {
     extern __shared__ __align__(16) uint8_t vit_smem[];
-    warp_body<MET, IN, BPP>(kp, blockIdx.x, blockIdx.y, (int)threadIdx.x, vit_smem);
+    warp_body<MET, IN, BPP, TBL>(kp, blockIdx.x, blockIdx.y, (int)threadIdx.x, vit_smem);
 }
 #endif
 

@@ -54,11 +54,15 @@ struct Job {
     unsigned warp, stream;
     uint8_t* smem;
     int met, in, bpp;
+    int tbl = 96;      // operand-table variant of the kernel: 96 (per super-step) or 32 (per slide)
 };
 Job g_job;
 
 template <int MET, int IN, int BPP>
-void run_lane(int lane) { vitk::warp_body<MET, IN, BPP>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem); }
+void run_lane(int lane) {
+    if (g_job.tbl == 32) vitk::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
+    else vitk::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
+}
 
 template <int MET, int IN>
 void run_lane_bpp(int lane) {
@@ -97,6 +101,8 @@ void run_warp() {
     swapcontext(&g_main, &g_ctx[0]);
 }
 }  // namespace
+
+extern "C" void vit_emu_set_table(int tbl) { g_job.tbl = tbl == 32 ? 32 : 96; }
 
 extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inputNum, unsigned segments,
                               unsigned nstreams, size_t in_stride, size_t out_stride) {

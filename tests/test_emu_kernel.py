@@ -40,6 +40,21 @@ def test_kernel_source_matches_oracle(emu, O, opt):
     run_case(emu, O, opt, 64 + 32 * 3 + 16, 8, seed=9, sigma=0.5)      # fewer packs than segments
 
 
+@pytest.mark.parametrize("opt", [0x011, 0x000, 0x121, 0x112, 0x004, 0x023])
+def test_kernel_source_small_table_variant(emu, O, opt):
+    """The TBL=32 build of the kernel (operand table rebuilt before every 32-stage slide; used for launches whose
+    warps do not all fit with the 96-stage table) decodes the same words."""
+    emu.vit_emu_set_table(32)
+    try:
+        run_case(emu, O, opt, 3000 + 64 + 7, 12, seed=5, sigma=0.9)
+        run_case(emu, O, opt, 1500 + 64, 5, seed=1, zero=True)
+        run_case(emu, O, opt, 64 + 32 * 3 + 16, 8, seed=9, sigma=0.5)
+        amp = {0: 64, 1: 7, 2: 127, 3: 32767, 4: 128}[opt & 0xF]
+        run_case(emu, O, opt, 12000 + 64, 4, seed=11, sigma=1.0, amp=amp)
+    finally:
+        emu.vit_emu_set_table(96)
+
+
 @pytest.mark.parametrize("opt", [0x012, 0x112, 0x011, 0x024, 0x022, 0x003])
 def test_kernel_source_long_segments(emu, O, opt):
     """Several 96-stage super-steps per segment, saturated symbols: exercises the metric range
