@@ -146,7 +146,7 @@ class ClockSampler:
     def __init__(self, index, period_ms=2):
         self.index, self.rows, self.proc, self.period_ms = index, [], None, period_ms
         self.t_mark = self.t_unmark = None
-        self.stop, self.t, self.nv, self.max_mhz, self.source = False, None, None, None, None
+        self.stop, self.t, self.nv, self.max_mhz, self.source, self.nq = False, None, None, None, None, 0
 
     def __enter__(self):
         try:
@@ -204,6 +204,7 @@ class ClockSampler:
                     pw = None
                 flags = ["Active" if mask & b else "Not Active" for b, _ in bits]
                 self.rows.append((time.perf_counter(), [str(self.index), str(mhz), str(self.max_mhz), str(pw), hex(mask)] + flags))
+                self.nq += 1
             except Exception:
                 pass
             time.sleep(self.period_ms / 1000.0)
@@ -320,7 +321,7 @@ def run_reference(args, options, n_bits, snr):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s4_b16_o32_32M", choices=sorted(WORKLOADS))
@@ -431,9 +432,15 @@ def main():
     launches0 = dec.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
-        for k in range(args.warmup):       # same kernels again: the sampler sees the load before the timed region too
+        # same kernels again, for at least 0.3 s: NVML answers a clock query in milliseconds to tens of milliseconds,
+        # so a short timed region alone may hold few samples; the sampler sees this identical load as well
+        k, t_load = 0, time.perf_counter()
+        while k < args.warmup or time.perf_counter() - t_load < 0.3:
             step(k)
-        drain(args.warmup - 1)
+            k += 1
+            if k % 64 == 0:
+                st.synchronize()
+        drain(k - 1)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

@@ -7,23 +7,28 @@
 //
 //   * 8 lanes per stream segment, 4 segments per warp (the reference: 32 lanes per segment).
 //     Each lane owns 8 trellis states: 4 packed int16x2 / half2 registers, or 8 int32 registers.
-//   * In-place "rotating" state map: position q (6 bits) holds state rotr6(q, phase) after a stage
-//     with phase = stage % 6.  q bits 0,2,4 are lane bits, q bits 1,3,5 are register/half bits, so
-//     only phases 1,3,5 need warp shuffles; phases 2,4 are register-local and phase 0 is a
-//     half-swap (packed cores) or register-local (int32 core).
+//   * The map (lane, register, half) -> trellis state is GF(2)-linear and changes with the stage (period 6) in
+//     such a way that EVERY butterfly joins two registers, or the two halves of one register, of the same
+//     lane.  Two stages of six need no data movement at all; before each of the other four every lane
+//     swaps half of its registers (2 metric + 4 survivor words) with lane ^ 1, 2, 4, 7 ("half exchange"):
+//     24 shuffles per 6 stages, where an in-place map that exchanges whole register sets on the three
+//     lane-bit stages needs 36.  See "trellis state <-> (lane, register, half) map" below.
 //   * A 96-stage super-step (lcm of the 6 phases and the 32-stage slide) is three straight-line
 //     slides, each a 5-iteration loop over the 6-stage phase period plus a 2-stage tail with the
 //     ring flush/traceback: shuffle masks, operand choices and row offsets are immediates, there is
-//     one loop branch per 6 stages, and the code (~15 KB) stays in the instruction cache.
+//     one loop branch per 6 stages, and the code (~25 KB) stays in the instruction cache.
 //   * Branch metrics: the channel words of the NEXT 96-stage super-step arrive by 16-byte cp.async
-//     into a raw staging area while the current super-step computes; once per super-step they are
-//     unpacked into a shared-memory table of ready-to-add packed operands (one 8-byte entry per
-//     stage x lane-class), so each ACS stage costs one LDS.64 per lane.
+//     into a raw staging area while the current super-step computes; they are unpacked into a
+//     shared-memory table of ready-to-add packed operands (one 8-byte entry per stage x lane-class;
+//     class 3-c holds the negated operands of class c), so each ACS stage costs two LDS.64 per lane.
+//     The table covers 96 stages (TBL=96, built once per super-step) or 32 (TBL=32, rebuilt before every
+//     slide: a third of the shared memory, twice the resident warps -- used by multi-stream launches).
 //   * Survivors: 32-bit register-exchange words moved with predicated selects (VIMNMX.S16x2 yields
-//     both decision predicates).  The decision bits themselves are never shifted in one by one:
-//     the last 6 message bits of a survivor are its state index, so they are OR-ed in as a 6-bit
-//     immediate field every 6 stages.
+//     both decision predicates; the int32 core derives the decision from a fused VIADDMNMX).  The
+//     decision bits themselves are never shifted in one by one: the last 6 message bits of a survivor
+//     are its state index, so they are merged in as a 6-bit field (one LOP3) every 6 stages.
 //   * The one-pointer ring (3 x 64 words per segment) lives in shared memory, not global.
+//   * Optional upload gates let one launch start before its input has arrived (vit_run's time-sliced copy-in).
 //
 // The same source compiles for the host (VIT_HOST_EMU) where 32 fibers run the warp in lockstep;
 // tests/emu uses that to check the kernel logic against the oracle without a GPU.  The host build
