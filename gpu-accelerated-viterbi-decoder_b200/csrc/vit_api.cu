@@ -371,6 +371,8 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
                 const size_t w2 = std::min(hi, pitch2);
                 if (w2 > lo)
                     VIT_CUDA(cudaMemcpy2DAsync(dst + grp2 + lo, pitch2, src + grp2 + lo, pitch2, w2 - lo, W - r, cudaMemcpyHostToDevice, h->copy_stream));
+                static const bool lose_gate = getenv("VIT_TEST_LOSE_GATE") != nullptr;   // test hook: never open the last gate
+                if (lose_gate && g + 1 == gp.n) continue;
                 VIT_CUDA(cudaMemcpyAsync(h->gate_d + g, h->epoch_h, sizeof(unsigned), cudaMemcpyHostToDevice, h->copy_stream));
             }
             static const bool dbg = getenv("VIT_RUN_DEBUG") != nullptr;

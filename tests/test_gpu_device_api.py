@@ -271,3 +271,33 @@ def test_host_run_time_sliced_upload(V, O, opt, n):
     got = h_out.numpy().view(dec.decPack_t)
     assert np.array_equal(got, exp)
     dec.close()
+
+
+def test_host_run_survives_a_lost_upload_gate():
+    """If a gate never opens (VIT_TEST_LOSE_GATE: the flag copy of the last column block is skipped) the kernel gives up
+    after ~2 s instead of hanging the GPU, and vit_run decodes again through the chunk pipeline: same output, no error."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from vit_testlib import load_pkg
+from oracle import oracle as O
+V = load_pkg()
+opt, n = 0x011, 6400 * 32 * 55 + 64
+bits, packed, N = O.make_channel_det(n, opt & 0xF, seed=3, sigma=0.7)
+dec = V.ViterbiCUDA(opt, N)
+h_in = torch.from_numpy(packed.view(np.uint8)[:dec.getInputSize(N)].copy()).pin_memory()
+h_out = torch.zeros(dec.getOutputSize(N), dtype=torch.uint8).pin_memory()
+for rep in range(2):
+    h_out.zero_()
+    dec.run(h_in.numpy(), N, output_h=h_out.numpy().view(dec.decPack_t))
+    assert np.array_equal(h_out.numpy().view(dec.decPack_t), O.decode(opt, packed, N)), rep
+print("OK launches", dec.launch_count())
+''' % (os.path.join(root, "tests"), root)
+    env = dict(os.environ, VIT_TEST_LOSE_GATE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK launches" in r.stdout, r.stdout + r.stderr
+    # 11.3 MB of input -> 2 chunks.  First run: 1 gated launch (abandoned) + 2 chunk launches; second run: gates
+    # disabled on the handle, 2 chunk launches
+    assert int(r.stdout.split()[-1]) == 5, r.stdout
