@@ -65,6 +65,8 @@ def lib():
         L.vit_dev_free.restype, L.vit_dev_free.argtypes = None, [vp]
         L.vit_dev_sync.restype, L.vit_dev_sync.argtypes = C.c_int, []
         L.vit_dev_count.restype, L.vit_dev_count.argtypes = C.c_int, []
+        L.vit_host_alloc.restype, L.vit_host_alloc.argtypes = C.c_int, [C.POINTER(vp), sz]
+        L.vit_host_free.restype, L.vit_host_free.argtypes = None, [vp]
         L.vit_synth_device.restype = C.c_int
         L.vit_synth_device.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, vp, vp, vp]
         _lib = L

@@ -156,6 +156,9 @@ int vit_dev_alloc(void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes ? byt
 void vit_dev_free(void* ptr) { if (ptr) cudaFree(ptr); }
 int vit_dev_sync(void) { return cudaDeviceSynchronize() == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
 int vit_dev_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+// page-locked host memory for callers without CUDA headers: vit_run takes its time-sliced upload path from such buffers
+int vit_host_alloc(void** ptr, size_t bytes) { return cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
+void vit_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
 #pragma GCC visibility pop
 }

@@ -106,6 +106,10 @@ int vit_dev_alloc(void** ptr, size_t bytes);
 void vit_dev_free(void* ptr);
 int vit_dev_sync(void);
 int vit_dev_count(void);
+/* page-locked (pinned) host memory: from such buffers vit_run overlaps upload, decode and download (one launch that waits for
+ * time slices of its input); pageable buffers take a slower segment-range chunk pipeline */
+int vit_host_alloc(void** ptr, size_t bytes);
+void vit_host_free(void* ptr);
 
 const char* vit_last_error(void);
 
