@@ -167,6 +167,154 @@ int launch(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t
 
 }  // namespace
 
+namespace {
+
+// geometry of one host-buffer decode (reference viterbi.cu:156-165 for the segment partition)
+struct HostRun {
+    const char* in_h; char* out_h;
+    size_t inputNum, in_bytes, out_bytes;
+    size_t bpp, W;            // bits per decoded pack, stream segments
+    size_t P, q, r;           // decoded packs; packs per segment; segments that are one pack longer
+    size_t b96;               // channel bytes per 96 trellis stages
+    size_t pack_bytes;        // channel bytes per decoded pack
+    size_t nsuper;            // 96-stage super-steps of the longest segment (64-stage tail included)
+    int nch;                  // chunks of the segment-range pipeline
+    size_t start_pack(size_t w) const { return q * w + std::min(w, r); }
+};
+
+HostRun host_run_geometry(const vit_handle* h, const void* in_h, void* out_h, size_t inputNum) {
+    const int o = h->options;
+    HostRun g;
+    g.in_h = static_cast<const char*>(in_h); g.out_h = static_cast<char*>(out_h);
+    g.inputNum = inputNum; g.in_bytes = vit_input_size(o, inputNum); g.out_bytes = vit_output_size(o, inputNum);
+    g.bpp = (size_t)bpp_of(o); g.W = h->segments;
+    g.P = vit_message_len(o, inputNum) / g.bpp; g.q = g.P / g.W; g.r = g.P % g.W;
+    g.b96 = in_type(o) == 0 ? 24 : in_type(o) == 1 ? 96 : in_type(o) == 2 ? 192 : in_type(o) == 3 ? 384 : 768;
+    g.pack_bytes = g.bpp * g.b96 / 96;
+    const size_t Lmax = (g.q + (g.r ? 1 : 0)) * g.bpp, Tmax = 64 + 32 * ((Lmax + 31) / 32);
+    g.nsuper = (Tmax + 95) / 96;
+    g.nch = (int)std::min<size_t>(vit_handle::MAX_CHUNKS, g.in_bytes / (4u << 20));
+    return g;
+}
+
+// host -> device (reference viterbi.cu:219), decode (viterbi.cu:228), device -> host (viterbi.cu:235);
+// kernel_ms = device time of the single decode launch, exactly the reference's measurement (viterbi.cu:224-232)
+int run_sequential(vit_handle* h, const HostRun& g, float* kernel_ms) {
+    VIT_CUDA(cudaMemcpyAsync(h->in_d, g.in_h, g.in_bytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = launch(h, h->in_d, h->out_d, g.inputNum, 1, 0, 0, h->stream, kernel_ms);
+    if (rc) return rc;
+    VIT_CUDA(cudaMemcpyAsync(g.out_h, h->out_d, g.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    VIT_CUDA(cudaStreamSynchronize(h->stream));
+    return VIT_OK;
+}
+
+bool gated_upload_applies(const vit_handle* h, const HostRun& g) {
+    if (h->gates_disabled || !h->gate_d || !h->gate_err_d) return false;
+    if (g.q < 1 || g.nsuper < 16 || g.in_bytes < (2u << 20)) return false;      // too short to be worth slicing
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, g.in_h) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;      // pageable memory is staged by the driver synchronously: no overlap to be had this way
+}
+
+// Time-sliced upload (pinned host input): ONE decode launch starts at once and every warp waits at "upload gates" for
+// the next column block of its segments; the copy stream uploads block b of EVERY segment (two strided copies: the
+// first P%W segments are one pack longer) and then opens gate b.  The decode therefore finishes one short block
+// after the last byte has landed, instead of a whole per-segment chain (0.25-0.4 ms) after it as with segment-range
+// chunks.  *gave_up is set when a warp stopped waiting for a gate (the output is then incomplete).
+int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
+    GatePlan gp;
+    // column blocks of 1/2, 3/8 and 1/8 of a segment (profiles/r1_upload_pattern_probe.txt): fewer, wider strided copies
+    // upload faster (0.66 ms for 32 MB against 0.69 with four blocks), a short last block keeps the tail short
+    gp.n = 3;
+    gp.super[0] = 0; gp.super[1] = (unsigned)(g.nsuper / 2); gp.super[2] = (unsigned)(g.nsuper * 7 / 8);
+    VIT_CUDA(cudaStreamSynchronize(h->stream));           // a kernel abandoned by a failed earlier call may still own the error word
+    h->epoch_h[16] = 0;
+    h->epoch++;
+    if (h->epoch == 0) h->epoch = 1;
+    *h->epoch_h = h->epoch;
+    static const bool dbg = getenv("VIT_RUN_DEBUG") != nullptr;
+    auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    const double t_begin = dbg ? now() : 0.0;
+    int rc = launch_range(h, h->in_d, h->out_d, g.inputNum, 1, 0, 0, h->stream, 0, (unsigned)g.W, nullptr, h->ev_kdone, &gp);
+    if (rc) return rc;
+    // (storing the decoded packs straight into pinned host memory instead was measured: 4-byte stores over PCIe double
+    // the time of the PCIe-bound s4 case)
+    VIT_CUDA(cudaMemcpyAsync(g.out_h, h->out_d, g.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    const char* src = g.in_h;
+    char* dst = static_cast<char*>(h->in_d);
+    const size_t pitch1 = (g.q + 1) * g.pack_bytes, pitch2 = g.q * g.pack_bytes;   // segment strides in bytes
+    const size_t grp2 = g.r * pitch1;                                                // first byte of segment r
+    const size_t body_end = g.P * g.pack_bytes;                                      // first byte after the last segment's own packs
+    // the last 64 stages of the stream (warm-up tail of the last segment) go with the first block
+    if (g.in_bytes > body_end)
+        VIT_CUDA(cudaMemcpyAsync(dst + body_end, src + body_end, g.in_bytes - body_end, cudaMemcpyHostToDevice, h->copy_stream));
+    static const bool lose_gate = getenv("VIT_TEST_LOSE_GATE") != nullptr;           // test hook: never open the last gate
+    for (unsigned b = 0; b < gp.n; b++) {
+        // columns [lo, hi) of every segment row: super-steps [super[b], super[b+1]) plus the read-ahead the kernel's
+        // 16-byte staging pieces take (<= 15 bytes before, <= 27 bytes after)
+        const size_t lo = b == 0 ? 0 : (size_t)gp.super[b] * g.b96 - 16;
+        const size_t hi = b + 1 == gp.n ? (size_t)-1 : (size_t)gp.super[b + 1] * g.b96 + 48;
+        const size_t w1 = std::min(hi, pitch1), w2 = std::min(hi, pitch2);
+        if (g.r && w1 > lo)
+            VIT_CUDA(cudaMemcpy2DAsync(dst + lo, pitch1, src + lo, pitch1, w1 - lo, g.r, cudaMemcpyHostToDevice, h->copy_stream));
+        if (w2 > lo)
+            VIT_CUDA(cudaMemcpy2DAsync(dst + grp2 + lo, pitch2, src + grp2 + lo, pitch2, w2 - lo, g.W - g.r, cudaMemcpyHostToDevice, h->copy_stream));
+        if (lose_gate && b + 1 == gp.n) continue;
+        VIT_CUDA(cudaMemcpyAsync(h->gate_d + b, h->epoch_h, sizeof(unsigned), cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    if (dbg) {
+        const double t_issued = now();
+        cudaStreamSynchronize(h->copy_stream);
+        const double t_copy = now();
+        cudaEventSynchronize(h->ev_kdone);
+        const double t_kernel = now();
+        cudaStreamSynchronize(h->stream);
+        fprintf(stderr, "[vit_run gated] issue %.3f ms, upload done +%.3f, kernel done +%.3f, download done +%.3f\n",
+                t_issued - t_begin, t_copy - t_begin, t_kernel - t_begin, now() - t_begin);
+    }
+    VIT_CUDA(cudaStreamSynchronize(h->copy_stream));
+    VIT_CUDA(cudaStreamSynchronize(h->stream));
+    *gave_up = *static_cast<volatile unsigned*>(h->epoch_h + 16) != 0;
+    h->epoch_h[16] = 0;
+    return VIT_OK;
+}
+
+// Segment-range chunk pipeline (pageable host input, or gates unavailable): the stream is cut at segment boundaries
+// into nch chunks (segments are independent: chunk i needs the input bytes up to the end of its last segment's tail
+// and produces a contiguous range of output packs).  Copies queue in order on one stream; each chunk's kernel runs on
+// its own stream as soon as its bytes have landed, so the kernels co-reside (all 1600 warps fit on the device at once)
+// instead of serialising.
+int run_chunked(vit_handle* h, const HostRun& g) {
+    size_t in_lo = 0;
+    for (int i = 0; i < g.nch; i++) {
+        const unsigned a = (unsigned)(g.W * i / g.nch / 4 * 4), b = (i + 1 == g.nch) ? (unsigned)g.W : (unsigned)(g.W * (i + 1) / g.nch / 4 * 4);
+        size_t in_hi = g.in_bytes;
+        if (i + 1 < g.nch) {
+            const size_t last_bits = (g.q + ((size_t)(b - 1) < g.r ? 1 : 0)) * g.bpp;
+            const size_t end_stage = g.start_pack(b - 1) * g.bpp + 64 + 32 * ((last_bits + 31) / 32) + 32;
+            in_hi = std::min(g.in_bytes, (end_stage * g.b96 + 95) / 96 + 64);
+            in_hi = std::max(in_hi, in_lo);
+        }
+        if (in_hi > in_lo)
+            VIT_CUDA(cudaMemcpyAsync(static_cast<char*>(h->in_d) + in_lo, g.in_h + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, h->copy_stream));
+        in_lo = in_hi;
+        VIT_CUDA(cudaEventRecord(h->ev_in[i], h->copy_stream));
+        VIT_CUDA(cudaStreamWaitEvent(h->chunk_stream[i], h->ev_in[i], 0));
+        int rc = launch_range(h, h->in_d, h->out_d, g.inputNum, 1, 0, 0, h->chunk_stream[i], a, b, nullptr, h->ev_k1[i]);
+        if (rc) return rc;
+        const size_t out_lo = g.start_pack(a) * g.bpp / 8, out_hi = (b >= g.W) ? g.out_bytes : g.start_pack(b) * g.bpp / 8;
+        VIT_CUDA(cudaStreamWaitEvent(h->out_stream, h->ev_k1[i], 0));
+        if (out_hi > out_lo)
+            VIT_CUDA(cudaMemcpyAsync(g.out_h + out_lo, static_cast<const char*>(h->out_d) + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, h->out_stream));
+    }
+    VIT_CUDA(cudaStreamSynchronize(h->out_stream));
+    for (int i = 0; i < g.nch; i++) VIT_CUDA(cudaStreamSynchronize(h->chunk_stream[i]));
+    return VIT_OK;
+}
+
+}  // namespace
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -307,132 +455,20 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
     if (out_bytes == 0) { if (kernel_ms) *kernel_ms = 0.f; return VIT_OK; }
     int rc = ensure_device_buffers(h, in_bytes, out_bytes);
     if (rc) return rc;
-    const int o = h->options;
-    const size_t bpp = (size_t)bpp_of(o), W = h->segments;
-    int nch = (int)std::min<size_t>(vit_handle::MAX_CHUNKS, in_bytes / (4u << 20));
-    if (kernel_ms || nch < 2 || W < 64) {
-        // host -> device (reference viterbi.cu:219), decode (viterbi.cu:228), device -> host (viterbi.cu:235);
-        // kernel_ms = device time of the single decode launch, exactly the reference's measurement (viterbi.cu:224-232)
-        VIT_CUDA(cudaMemcpyAsync(h->in_d, in_h, in_bytes, cudaMemcpyHostToDevice, h->stream));
-        rc = launch(h, h->in_d, h->out_d, inputNum, 1, 0, 0, h->stream, kernel_ms);
-        if (rc) return rc;
-        VIT_CUDA(cudaMemcpyAsync(out_h, h->out_d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
-        VIT_CUDA(cudaStreamSynchronize(h->stream));
-        return VIT_OK;
-    }
+    const HostRun hr = host_run_geometry(h, in_h, out_h, inputNum);
+    // VIT_RUN_MODE=2 (measurement hook) forces the segment-range chunk pipeline where the time-sliced upload would be used
     static const int run_mode = [] { const char* e = getenv("VIT_RUN_MODE"); return e ? atoi(e) : 0; }();
-    if (run_mode == 0) {       // VIT_RUN_MODE=2 (measurement hook) forces the segment-range chunk pipeline below
-        // Time-sliced upload (pinned host input): ONE decode launch starts at once and every warp waits at
-        // "upload gates" for the next column block of its segments; the copy stream uploads block g of EVERY
-        // segment (two strided copies: the first P%W segments are one pack longer) and then opens gate g.  The
-        // decode therefore finishes one short block after the last byte has landed, instead of a whole
-        // per-segment chain (0.25-0.4 ms) after it as with segment-range chunks.
-        cudaPointerAttributes pa;
-        const bool pinned = cudaPointerGetAttributes(&pa, in_h) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        const size_t P = vit_message_len(o, inputNum) / bpp, q = P / W, r = P % W;
-        const size_t b96 = in_type(o) == 0 ? 24 : in_type(o) == 1 ? 96 : in_type(o) == 2 ? 192 : in_type(o) == 3 ? 384 : 768;
-        const size_t Lmax = (q + (r ? 1 : 0)) * bpp, Tmax = 64 + 32 * ((Lmax + 31) / 32), nsuper = (Tmax + 95) / 96;
-        const size_t pack_bytes = bpp * b96 / 96;                 // channel bytes per decoded pack
-        if (pinned && !h->gates_disabled && q >= 1 && nsuper >= 16 && h->gate_d && h->gate_err_d && in_bytes >= (2u << 20)) {
-            GatePlan gp;
-            // column blocks of 1/2, 3/8 and 1/8 of a segment: scripts/upload_pattern_probe.cu -- fewer, wider strided copies
-            // upload faster (0.66 ms for 32 MB against 0.69 with four blocks), a short last block keeps the tail short
-            gp.n = 3;
-            gp.super[0] = 0; gp.super[1] = (unsigned)(nsuper / 2); gp.super[2] = (unsigned)(nsuper * 7 / 8);
-            h->epoch++;
-            if (h->epoch == 0) h->epoch = 1;
-            *h->epoch_h = h->epoch;
-            timespec tb; clock_gettime(CLOCK_MONOTONIC, &tb);
-            const double t_begin = tb.tv_sec * 1e3 + tb.tv_nsec * 1e-6;
-            rc = launch_range(h, h->in_d, h->out_d, inputNum, 1, 0, 0, h->stream, 0, (unsigned)W, nullptr, h->ev_kdone, &gp);
-            if (rc) return rc;
-            // (storing the decoded packs straight into pinned host memory instead was measured: 4-byte stores over PCIe
-            // double the time of the PCIe-bound s4 case)
-            VIT_CUDA(cudaMemcpyAsync(out_h, h->out_d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
-            const char* src = static_cast<const char*>(in_h);
-            char* dst = static_cast<char*>(h->in_d);
-            const size_t pitch1 = (q + 1) * pack_bytes, pitch2 = q * pack_bytes;     // segment strides in bytes
-            const size_t grp2 = r * pitch1;                                          // first byte of segment r
-            const size_t body_end = P * pack_bytes;                                  // first byte after the last segment's own packs
-            // the last 64 stages of the stream (warm-up tail of the last segment) go with the first block
-            if (in_bytes > body_end)
-                VIT_CUDA(cudaMemcpyAsync(dst + body_end, src + body_end, in_bytes - body_end, cudaMemcpyHostToDevice, h->copy_stream));
-            for (unsigned g = 0; g < gp.n; g++) {
-                // columns [lo, hi) of every segment row: super-steps [super[g], super[g+1]) plus the read-ahead the
-                // kernel's 16-byte staging pieces take (<= 15 bytes before, <= 27 bytes after)
-                const size_t lo = g == 0 ? 0 : (size_t)gp.super[g] * b96 - 16;
-                const size_t hi = g + 1 == gp.n ? (size_t)-1 : (size_t)gp.super[g + 1] * b96 + 48;
-                if (r) {
-                    const size_t w1 = std::min(hi, pitch1);
-                    if (w1 > lo)
-                        VIT_CUDA(cudaMemcpy2DAsync(dst + lo, pitch1, src + lo, pitch1, w1 - lo, r, cudaMemcpyHostToDevice, h->copy_stream));
-                }
-                const size_t w2 = std::min(hi, pitch2);
-                if (w2 > lo)
-                    VIT_CUDA(cudaMemcpy2DAsync(dst + grp2 + lo, pitch2, src + grp2 + lo, pitch2, w2 - lo, W - r, cudaMemcpyHostToDevice, h->copy_stream));
-                static const bool lose_gate = getenv("VIT_TEST_LOSE_GATE") != nullptr;   // test hook: never open the last gate
-                if (lose_gate && g + 1 == gp.n) continue;
-                VIT_CUDA(cudaMemcpyAsync(h->gate_d + g, h->epoch_h, sizeof(unsigned), cudaMemcpyHostToDevice, h->copy_stream));
-            }
-            static const bool dbg = getenv("VIT_RUN_DEBUG") != nullptr;
-            if (dbg) {
-                auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
-                const double t_issued = now();
-                cudaStreamSynchronize(h->copy_stream);
-                const double t_copy = now();
-                cudaEventSynchronize(h->ev_kdone);
-                const double t_kernel = now();
-                cudaStreamSynchronize(h->stream);
-                const double t_all = now();
-                fprintf(stderr, "[vit_run gated] issue %.3f ms, upload done +%.3f, kernel done +%.3f, download done +%.3f\n",
-                        t_issued - t_begin, t_copy - t_begin, t_kernel - t_begin, t_all - t_begin);
-            }
-            VIT_CUDA(cudaStreamSynchronize(h->copy_stream));
-            VIT_CUDA(cudaStreamSynchronize(h->stream));
-            if (*static_cast<volatile unsigned*>(h->epoch_h + 16) == 0) return VIT_OK;
-            // A warp gave up waiting for its upload gate: something (a profiler or sanitizer that serialises kernels
-            // and copies, an exhausted copy queue) kept the copies from running beside the kernel.  Nothing was lost:
-            // decode again with the chunk pipeline below and stop using gates on this handle.
-            h->epoch_h[16] = 0;
-            h->gates_disabled = true;
-        }
+    if (kernel_ms || hr.nch < 2 || hr.W < 64) return run_sequential(h, hr, kernel_ms);
+    if (run_mode == 0 && gated_upload_applies(h, hr)) {
+        bool gave_up = false;
+        rc = run_gated(h, hr, &gave_up);
+        if (rc || !gave_up) return rc;
+        // A warp gave up waiting for its upload gate: something (a profiler that serialises kernels and copies, an
+        // exhausted copy queue) kept the copies from running beside the kernel.  Nothing was lost: decode again with
+        // the chunk pipeline and stop using gates on this handle.
+        h->gates_disabled = true;
     }
-    // No timing requested: overlap the three phases.  The stream is cut at segment boundaries into nch
-    // chunks (segments are independent: chunk i needs the input bytes up to the end of its last segment's
-    // tail and produces a contiguous range of output packs).  Copies queue in order on one stream; each
-    // chunk's kernel runs on its own stream as soon as its bytes have landed, so the kernels co-reside
-    // (all 1600 warps fit on the device at once) instead of serialising.
-    const size_t P = vit_message_len(o, inputNum) / bpp, q = P / W, r = P % W;
-    const size_t b96 = in_type(o) == 0 ? 24 : in_type(o) == 1 ? 96 : in_type(o) == 2 ? 192 : in_type(o) == 3 ? 384 : 768;
-    auto start_pack = [&](size_t w) { return q * w + std::min(w, r); };
-    size_t in_lo = 0;
-    for (int i = 0; i < nch; i++) {
-        const unsigned a = (unsigned)(W * i / nch / 4 * 4), b = (i + 1 == nch) ? (unsigned)W : (unsigned)(W * (i + 1) / nch / 4 * 4);
-        size_t in_hi = in_bytes;
-        if (i + 1 < nch) {
-            const size_t last_bits = (q + ((size_t)(b - 1) < r ? 1 : 0)) * bpp;
-            const size_t end_stage = start_pack(b - 1) * bpp + 64 + 32 * ((last_bits + 31) / 32) + 32;
-            in_hi = std::min(in_bytes, (end_stage * b96 + 95) / 96 + 64);
-            in_hi = std::max(in_hi, in_lo);
-        }
-        if (in_hi > in_lo)
-            VIT_CUDA(cudaMemcpyAsync(static_cast<char*>(h->in_d) + in_lo, static_cast<const char*>(in_h) + in_lo,
-                                     in_hi - in_lo, cudaMemcpyHostToDevice, h->copy_stream));
-        in_lo = in_hi;
-        VIT_CUDA(cudaEventRecord(h->ev_in[i], h->copy_stream));
-        VIT_CUDA(cudaStreamWaitEvent(h->chunk_stream[i], h->ev_in[i], 0));
-        rc = launch_range(h, h->in_d, h->out_d, inputNum, 1, 0, 0, h->chunk_stream[i], a, b, nullptr, h->ev_k1[i]);
-        if (rc) return rc;
-        const size_t out_lo = start_pack(a) * bpp / 8, out_hi = (b >= W) ? out_bytes : start_pack(b) * bpp / 8;
-        VIT_CUDA(cudaStreamWaitEvent(h->out_stream, h->ev_k1[i], 0));
-        if (out_hi > out_lo)
-            VIT_CUDA(cudaMemcpyAsync(static_cast<char*>(out_h) + out_lo, static_cast<const char*>(h->out_d) + out_lo,
-                                     out_hi - out_lo, cudaMemcpyDeviceToHost, h->out_stream));
-    }
-    VIT_CUDA(cudaStreamSynchronize(h->out_stream));
-    for (int i = 0; i < nch; i++) VIT_CUDA(cudaStreamSynchronize(h->chunk_stream[i]));
-    return VIT_OK;
+    return run_chunked(h, hr);
 }
 
 #pragma GCC visibility pop
