@@ -311,7 +311,7 @@ def run_reference(args, options, n_bits, snr):
         "gpu_launches": args.steps, "clocks": cs.summary(),
         "e2e": {"value": M * args.steps / wall / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": int(O.input_size(options, N)),
                 "d2h_bytes_per_step": int(O.output_size(options, N))},
-        "cpu_baseline": {"value": None, "unit": "Gb/s", "cores": 0, "kind": "reference",
+        "cpu_baseline": {"value": M / (statistics.mean(kms) * 1e6), "unit": "Gb/s", "cores": 0, "kind": "reference",
                          "sample": "reference CUDA decoder (oracle/_ref/libvitref.so, -arch=sm_100) on GPU 0; value = its own cudaEvent kernel time, "
                                    "e2e = wall clock of ViterbiCUDA::run incl. its cudaMalloc/cudaMemcpy/cudaFree"},
     })
