@@ -164,6 +164,9 @@ template <int IN> constexpr int raw_pieces() { return (InTraits<IN>::B96 + 12 + 
 // offset added to int16 branch metrics so every packed operand is a non-negative 16-bit value
 // (lets plain 32-bit adds act as two independent 16-bit adds); == max |symbol sum| / 1
 template <int IN> constexpr int b16_offset() { return IN == IN_HARD ? 1 : IN == IN_S8 ? 256 : 16; }
+// the same for the half2 core (s8/s16 symbols are pre-scaled to 5 bits there): operands and metrics stay non-negative,
+// so their IEEE bit patterns order like integers and VIMNMX.S16x2 can do the compare (see Core<MET_F16>)
+template <int IN> constexpr int f16_offset() { return IN == IN_HARD ? 1 : (IN == IN_S8 || IN == IN_S16) ? 32 : 16; }
 
 // shared memory carve-up (per warp; one warp per block)
 // Operand table: row (stage) = 4 segments x 4 lane classes x 8 B = 128 B; rows are grouped by
@@ -361,16 +364,23 @@ template <int IN> struct Core<MET_F16, IN> {
     static VIT_D __half2 h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
     static VIT_D uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
     static VIT_D uint32_t plus(uint32_t pm, uint32_t w, uint32_t) { return u32(__hadd2(h2(pm), h2(w))); }
-    // own wins ties (reference half2 core, viterbiACS.cuh:146-157,249-256: __hlt2_mask(own, partner)):
-    // partner chosen iff partner > own.  HMNMX2 + HSETP2 (two predicates), then SEL or predicated IMAD.
+    // Metric adds are HADD2 on the FP16 pipe; values are exact integers in [0, 2048).  Operands carry a +offset, so
+    // every candidate is a non-negative half and compares like its bit pattern: the compare/select is the same single
+    // VIMNMX.S16x2 Rd, P0, P1 as in the int16x2 core (HMNMX2 + HSETP2 would be two instructions).
+    // own wins ties (reference half2 core, viterbiACS.cuh:146-157,249-256: __hlt2_mask(own, partner)): the maximum is
+    // taken with the own candidate first and "own chosen" = (max == own).
     static VIT_D uint32_t acs_sel(uint32_t part, uint32_t own, uint32_t keep_lo, uint32_t src_lo, uint32_t keep_hi,
                                   uint32_t src_hi, uint32_t& out_lo, uint32_t& out_hi, bool) {
         uint32_t v;
         asm("{.reg .pred pl, ph; \n\t"
-            "max.f16x2 %0, %3, %4; \n\t"
-            "setp.gt.f16x2 pl|ph, %3, %4; \n\t"
-            "selp.b32 %1, %6, %5, pl; \n\t"
-            "selp.b32 %2, %8, %7, ph;} \n\t"
+            ".reg .s16 rs0, rs1, rs2, rs3; \n\t"
+            "max.s16x2 %0, %4, %3; \n\t"
+            "mov.b32 {rs0, rs1}, %0; \n\t"
+            "mov.b32 {rs2, rs3}, %4; \n\t"
+            "setp.eq.s16 pl, rs0, rs2; \n\t"
+            "setp.eq.s16 ph, rs1, rs3; \n\t"
+            "selp.b32 %1, %5, %6, pl; \n\t"
+            "selp.b32 %2, %7, %8, ph;} \n\t"
             : "=r"(v), "=r"(out_lo), "=r"(out_hi)
             : "r"(part), "r"(own), "r"(keep_lo), "r"(src_lo), "r"(keep_hi), "r"(src_hi));
         return v;
@@ -379,17 +389,21 @@ template <int IN> struct Core<MET_F16, IN> {
                                   uint32_t src_hi, uint32_t one, bool) {
         uint32_t v;
         asm("{.reg .pred pl, ph; \n\t"
-            "max.f16x2 %0, %3, %4; \n\t"
-            "setp.gt.f16x2 pl|ph, %3, %4; \n\t"
-            "@pl mad.lo.u32 %1, %5, %7, 0; \n\t"
-            "@ph mad.lo.u32 %2, %6, %7, 0;} \n\t"
+            ".reg .s16 rs0, rs1, rs2, rs3; \n\t"
+            "max.s16x2 %0, %4, %3; \n\t"
+            "mov.b32 {rs0, rs1}, %0; \n\t"
+            "mov.b32 {rs2, rs3}, %4; \n\t"
+            "setp.eq.s16 pl, rs0, rs2; \n\t"
+            "setp.eq.s16 ph, rs1, rs3; \n\t"
+            "@!pl mad.lo.u32 %1, %5, %7, 0; \n\t"
+            "@!ph mad.lo.u32 %2, %6, %7, 0;} \n\t"
             : "=r"(v), "+r"(io_lo), "+r"(io_hi)
             : "r"(part), "r"(own), "r"(src_lo), "r"(src_hi), "r"(one));
         return v;
     }
     static VIT_D uint32_t vmin(uint32_t a, uint32_t b) { return u32(__hmin2(h2(a), h2(b))); }
     static VIT_D uint32_t sub(uint32_t a, uint32_t m) { return u32(__hsub2(h2(a), h2(m))); }
-    static VIT_D uint32_t enc(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v)); }
+    static VIT_D uint32_t enc(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v + f16_offset<IN>())); }
 #else
     static uint32_t plus(uint32_t pm, uint32_t w, uint32_t) { EmuH2 a = emu_h2_unpack(pm), b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{a.lo + b.lo, a.hi + b.hi}); }
     static uint32_t neg(uint32_t w, uint32_t) { EmuH2 b = emu_h2_unpack(w); return emu_h2_pack(EmuH2{-b.lo, -b.hi}); }
@@ -415,7 +429,7 @@ template <int IN> struct Core<MET_F16, IN> {
     }
     static uint32_t vmin(uint32_t a, uint32_t b) { EmuH2 x = emu_h2_unpack(a), y = emu_h2_unpack(b); return emu_h2_pack(EmuH2{x.lo < y.lo ? x.lo : y.lo, x.hi < y.hi ? x.hi : y.hi}); }
     static uint32_t sub(uint32_t a, uint32_t m) { return plus(a, neg(m, 1), 1); }
-    static uint32_t enc(int v) { return (uint32_t)(uint16_t)(int16_t)v; }
+    static uint32_t enc(int v) { return (uint32_t)(uint16_t)(int16_t)(v + f16_offset<IN>()); }
 #endif
     static VIT_HD uint32_t zero() { return 0; }
 };
@@ -825,9 +839,13 @@ VIT_HD void normalize(LaneState<MET>& s) {
     for (int r = 0; r < LaneState<MET>::NPM; r++) s.pm[r] = C::sub(s.pm[r], m);
 }
 
-// stages per normalization (must divide 96 and be a multiple of 32)
+// stages per normalization: 96 (super-step start), 32 (slide end) or 16 (slide end and after its third loop iteration).
+// int16x2: offsets grow a metric by <= 2*offset per stage and it must stay below 2^15; half2: below 2048 (exact integers):
+// hard 2*96 + 12, s4/fp32 32*32 + 192, s8/s16 (5-bit symbols, offset 32) 64*18 + 384.
 template <int MET, int IN> constexpr int norm_period() {
-    return (MET == MET_B16 && IN == IN_S8) ? 32 : (MET == MET_F16 && (IN == IN_S8 || IN == IN_S16)) ? 32 : 96;
+    return (MET == MET_B16) ? (IN == IN_S8 ? 32 : 96)
+         : (MET == MET_F16) ? (IN == IN_HARD ? 96 : (IN == IN_S8 || IN == IN_S16) ? 16 : 32)
+         : 96;
 }
 
 // End of a 32-stage slide (superchunk stage S = 32*SLOT + 31, phase P = S % 6): flush the
@@ -869,7 +887,7 @@ VIT_HD void slide_end(WarpCtx<MET, IN, BPP, TBL>& c) {
     }
     // start the next word: message bits e-5..e are the state index
     insert_field<MET, P, 26, 6, true>(c.st, c.lane_field[P / 2]);
-    if constexpr (norm_period<MET, IN>() == 32) normalize<MET, IN>(c.st);
+    if constexpr (norm_period<MET, IN>() <= 32) normalize<MET, IN>(c.st);
 }
 
 // i-th insertion batch of a survivor word (i = 0..4), all at phase P: 6 bits at 20,14,8,2, then 2 bits at 0
@@ -922,6 +940,9 @@ VIT_HD bool slide(WarpCtx<MET, IN, BPP, TBL>& c, unsigned Tmax) {
         one_stage<MET, IN, BPP, TBL, S0 + 4>(c, tbl);
         one_stage<MET, IN, BPP, TBL, S0 + 5>(c, tbl);
         insert_batch<MET, PB>(c.st, c.lane_field[PB / 2], i);
+        if constexpr (norm_period<MET, IN>() == 16) {
+            if (i == 2) normalize<MET, IN>(c.st);
+        }
     }
     one_stage<MET, IN, BPP, TBL, S0 + 30>(c, c.smem + SM::OFF_BM);
     one_stage<MET, IN, BPP, TBL, S0 + 31>(c, c.smem + SM::OFF_BM);
@@ -1017,7 +1038,7 @@ VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int 
             syncwarp();
             VIT_PREFETCH
         }
-        if constexpr (norm_period<MET, IN>() != 32) normalize<MET, IN>(c.st);
+        if constexpr (norm_period<MET, IN>() == 96) normalize<MET, IN>(c.st);
         if constexpr (TBL == 32) build_slide<MET, IN, BPP, TBL, 0>(c, skew);
         if (slide<MET, IN, BPP, TBL, 0>(c, Tmax)) break;
         if constexpr (TBL == 32) build_slide<MET, IN, BPP, TBL, 1>(c, skew);
