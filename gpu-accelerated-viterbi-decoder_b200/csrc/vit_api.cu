@@ -139,9 +139,8 @@ int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, 
         kp.gate_n = gp->n;
         for (unsigned i = 0; i < gp->n; i++) kp.gate_super[i] = gp->super[i];
     }
-    dim3 grid((seg_limit - seg_first + vitk::SEGS_PER_WARP - 1) / vitk::SEGS_PER_WARP, (unsigned)nstreams, 1);
     if (e0) VIT_CUDA(cudaEventRecord(e0, st));
-    VIT_CUDA(h->kernel->launch(kp, grid, st));
+    VIT_CUDA(h->kernel->launch(kp, st));
     h->launches++;
     if (e1) VIT_CUDA(cudaEventRecord(e1, st));
     return VIT_OK;
@@ -288,7 +287,7 @@ int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
 int run_chunked(vit_handle* h, const HostRun& g) {
     size_t in_lo = 0;
     for (int i = 0; i < g.nch; i++) {
-        const unsigned a = (unsigned)(g.W * i / g.nch / 4 * 4), b = (i + 1 == g.nch) ? (unsigned)g.W : (unsigned)(g.W * (i + 1) / g.nch / 4 * 4);
+        const unsigned a = (unsigned)(g.W * i / g.nch / 8 * 8), b = (i + 1 == g.nch) ? (unsigned)g.W : (unsigned)(g.W * (i + 1) / g.nch / 8 * 8);
         size_t in_hi = g.in_bytes;
         if (i + 1 < g.nch) {
             const size_t last_bits = (g.q + ((size_t)(b - 1) < g.r ? 1 : 0)) * g.bpp;
@@ -364,7 +363,7 @@ int vit_kernel_info(int o, int* regs, int* smem_bytes, int* block_threads, int* 
     if (regs) *regs = a.numRegs;
     if (smem_bytes) *smem_bytes = e->smem_bytes;
     if (block_threads) *block_threads = 32;
-    if (segs_per_block) *segs_per_block = vitk::SEGS_PER_WARP;
+    if (segs_per_block) *segs_per_block = vitk::l8::SEGS_PER_WARP;     // single-stream build; multi-stream launches: l4, 8
     return VIT_OK;
 }
 

@@ -37,6 +37,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <utility>
 
 #if defined(__CUDACC__)
 #include <cuda_fp16.h>
@@ -79,79 +80,8 @@ struct KParams {
 // compile-time trellis geometry
 // ------------------------------------------------------------------------------------------------
 constexpr int mod6(int x) { return ((x % 6) + 6) % 6; }
-constexpr int LANES_PER_SEG = 8;
-constexpr int SEGS_PER_WARP = 4;
 constexpr int SUPER = 96;       // unroll period
-
-// ------------------------------------------------------------------------------------------------
-// trellis state <-> (lane, register, half) map
-//
-// A position is a 6-bit vector v = [l0 l1 l2 | r0 r1 r2]: l = lane within the 8-lane group, r0 r1 = packed
-// register index, r2 = half of the packed register (int32 core: third register-index bit).  At every
-// stage the map position -> state is GF(2)-linear: state bit i = parity(v & f_i).  A trellis stage pairs
-// the two positions that differ only in state bit 0 (the butterfly) and writes the two new states back
-// in place, the new MSB u taking the value the position's old state bit 0 had, so the six functionals
-// just rotate (f_i <- f_{i+1}, f_5 <- f_0).  The map is chosen so that every butterfly joins two
-// registers (or the two halves of one register) of the SAME lane:
-//
-//   phase 0: butterfly along r1            (no data movement)
-//   phase 1: butterfly along r2            (half swap for the packed cores)
-//   phase 2..5: butterfly along r0, each preceded by a "half exchange": every lane sends its r0=1 registers
-//               (2 metric + 4 survivor registers) to lane ^ m, m = 1, 2, 4, 7, and keeps its r0=0 registers.
-//
-// The half exchange is the transvection v -> v + r0(v)*m of the position space: it substitutes
-// l -> l + r0*m in every functional, so that the functional about to become state bit 0 has a dual vector
-// without lane component.  The masks sum to zero (1^2^4^7), so the map has period 6 and everything below
-// is a compile-time function of the phase.  24 shuffles per 6 stages instead of the 36 of a map that
-// exchanges all 12 registers on the three lane-bit stages.
-// ------------------------------------------------------------------------------------------------
-constexpr int PB_R0 = 8, PB_R1 = 16, PB_R2 = 32;
-constexpr int par6(int v) { return ((v >> 0) ^ (v >> 1) ^ (v >> 2) ^ (v >> 3) ^ (v >> 4) ^ (v >> 5)) & 1; }
-constexpr int xmask_of(int p) { return p == 2 ? 1 : p == 3 ? 2 : p == 4 ? 4 : p == 5 ? 7 : 0; }   // exchange before stage p
-constexpr int cum_of(int p) { return p == 2 ? 1 : p == 3 ? 3 : p == 4 ? 7 : 0; }                   // sum of the masks so far
-constexpr int lprime(int j, int c) { return (1 << j) | (((c >> j) & 1) ? PB_R0 : 0); }              // l_j + r0*c_j
-// slot q = the functional whose butterfly is done at phase q, under accumulated exchange offset c
-constexpr int func_of_slot(int q, int c) {
-    return q == 0 ? PB_R1 : q == 1 ? PB_R2 : q == 2 ? (lprime(0, c) ^ lprime(1, c)) : q == 3 ? (lprime(1, c) ^ lprime(2, c))
-         : q == 4 ? lprime(2, c) : (PB_R0 ^ lprime(0, c));
-}
-// ... and its dual position vector (flips that state bit only)
-constexpr int dual_of_slot(int q, int c) {
-    return q == 0 ? PB_R1 : q == 1 ? PB_R2 : q == 2 ? ((1 ^ c) | PB_R0) : q == 3 ? ((3 ^ c) | PB_R0) : q == 4 ? ((7 ^ c) | PB_R0) : (c | PB_R0);
-}
-constexpr int f_before(int p, int i) { return func_of_slot(mod6(p + i), cum_of(p)); }      // state bit i entering stage p
-constexpr int f_after(int p, int i) { return func_of_slot(mod6(p + 1 + i), cum_of(p)); }   // state bit i leaving stage p
-
-// Own-branch symbol of a position entering stage p.  The encoder register is (u<<6)|S with u = S bit 0,
-// and both polynomials tap bits 0 and 6, so symbol bit 0 (poly 0171) = S3^S4^S5, symbol bit 1 (poly 0133) = S1^S3^S4.
-constexpr int sym_func(int which, int p) {
-    return which == 0 ? (f_before(p, 3) ^ f_before(p, 4) ^ f_before(p, 5)) : (f_before(p, 1) ^ f_before(p, 3) ^ f_before(p, 4));
-}
-constexpr int reg_mask(int which, int p) { return (sym_func(which, p) >> 3) & 7; }
-constexpr int par3(int v) { return ((v >> 0) ^ (v >> 1) ^ (v >> 2)) & 1; }
-
-// operand type of the own-branch metric for register index s8 at phase p:
-//   0: +X   1: +Y   2: -Y   3: -X      (X = D0+D1, Y = D0-D1 of the lane-class adjusted symbols)
-constexpr int bm_type(int s8, int p) {
-    int st0 = par3(s8 & reg_mask(0, p)), st1 = par3(s8 & reg_mask(1, p));
-    return st0 == 0 ? (st1 == 0 ? 0 : 1) : (st1 == 0 ? 2 : 3);
-}
-// how the high half of a packed operand differs from the low half (does r2 enter symbol bit 0 / 1)
-constexpr int half_variant(int p) { return ((sym_func(0, p) & PB_R2) ? 2 : 0) | ((sym_func(1, p) & PB_R2) ? 1 : 0); }
-
-// stage kinds
-enum { KIND_HALF = 0, KIND_REG = 2 };
-template <int MET>
-constexpr int stage_kind(int p) { return (p == 1 && MET != MET_B32) ? KIND_HALF : KIND_REG; }
-constexpr int stage_bit(int p) { return p == 0 ? 1 : p == 1 ? 2 : 0; }  // register-index bit of the butterfly
-
-// 6-bit survivor field (oldest message bit = state bit 0 in the MSB) of register s8 leaving stage p; the
-// lane's part (lane_field_of) is XOR-ed in at run time
-constexpr int static_field(int s8, int p) {
-    int f = 0;
-    for (int i = 0; i < 6; i++) if (par3(s8 & (f_after(p, i) >> 3))) f |= 1 << (5 - i);
-    return f;
-}
+constexpr int par3(int v) { return ((v >> 0) ^ (v >> 1) ^ (v >> 2) ^ (v >> 3)) & 1; }   // parity of up to 4 bits
 
 template <int IN> struct InTraits;
 template <> struct InTraits<IN_HARD> { static constexpr int B96 = 24; };
@@ -167,34 +97,6 @@ template <int IN> constexpr int b16_offset() { return IN == IN_HARD ? 1 : IN == 
 // the same for the half2 core (s8/s16 symbols are pre-scaled to 5 bits there): operands and metrics stay non-negative,
 // so their IEEE bit patterns order like integers and VIMNMX.S16x2 can do the compare (see Core<MET_F16>)
 template <int IN> constexpr int f16_offset() { return IN == IN_HARD ? 1 : (IN == IN_S8 || IN == IN_S16) ? 32 : 16; }
-
-// shared memory carve-up (per warp; one warp per block)
-// Operand table: row (stage) = 4 segments x 4 lane classes x 8 B = 128 B; rows are grouped by
-// j = stage/6 and each j-block is padded by 16 B so that the 8 lanes of a group, which build rows
-// 6 apart, store to 8 different 16-byte bank columns (conflict-free STS.128).
-constexpr int BM_ROW = SEGS_PER_WARP * 4 * 8;            // 128
-constexpr int BM_JBLOCK = 6 * BM_ROW + 16;               // 784
-// stage within the super-step -> table row.  TBL = stages the table holds: 96 (built once per super-step) or 32
-// (rebuilt before every slide: 1/3 of the shared memory, twice the resident warps, for multi-stream launches)
-template <int TBL>
-constexpr int row_off(int s) { return ((s % TBL) / 6) * BM_JBLOCK + ((s % TBL) % 6) * BM_ROW; }
-// Ring: per (slot, segment) 64 words + 16 B pad; lane l stores its 8 words at l*32 + (l>>2)*16 so that
-// the two STS.128 of a flush are conflict-free as well.
-constexpr int RING_SEG = 64 * 4 + 16;                    // 272
-constexpr int ring_word_of(int l, int r) { return l * 8 + (l >> 2) * 4 + r; }
-
-template <int IN, int TBL = 96> struct Smem {
-    static constexpr int BM_BYTES = ((TBL + 5) / 6) * BM_JBLOCK;                   // 12544 | 4704
-    static constexpr int RAW_SEG = raw_pieces<IN>() * 16;
-    static constexpr int RAW_BYTES = SEGS_PER_WARP * RAW_SEG;      // single buffer: consumed whole by the table build
-    static constexpr int RING_BYTES = 3 * SEGS_PER_WARP * RING_SEG;                // 3264
-    static constexpr int LUT_BYTES = 3 * 64;
-    static constexpr int OFF_BM = 0;
-    static constexpr int OFF_RAW = OFF_BM + BM_BYTES;
-    static constexpr int OFF_RING = OFF_RAW + RAW_BYTES;
-    static constexpr int OFF_LUT = OFF_RING + RING_BYTES;
-    static constexpr int TOTAL = OFF_LUT + LUT_BYTES;
-};
 
 // ------------------------------------------------------------------------------------------------
 // SIMT primitives: device intrinsics, or the host emulator's lockstep fibers
@@ -511,15 +413,6 @@ template <int IN> struct Core<MET_B32, IN> {
     static VIT_HD uint32_t zero() { return 0; }
 };
 
-// ------------------------------------------------------------------------------------------------
-// per-lane decoder state
-// ------------------------------------------------------------------------------------------------
-template <int MET> struct LaneState {
-    static constexpr int NPM = (MET == MET_B32) ? 8 : 4;
-    uint32_t pm[NPM];
-    uint32_t pp[8];
-};
-
 // candidate of `metric` along the branch whose operand type is `type` (see bm_type), given the
 // table entry (w0 = X word, w1 = Y word); `opposite` = the other branch into the same state
 struct Operands { uint32_t x, y, nx, ny, one; };   // +X, +Y, -X, -Y in the core's operand encoding
@@ -538,63 +431,6 @@ VIT_HD uint32_t cand(uint32_t metric, const Operands& o) {
     return C::plus(metric, neg ? (useY ? o.ny : o.nx) : (useY ? o.y : o.x), o.one);
 }
 
-// one trellis stage at phase P (static).  lane bits are the low 3 bits of the lane id.
-// Survivor selects alternate between the SEL form (ALU pipe) and the predicated-IMAD form (FMA pipe).
-template <int MET, int IN, int P>
-VIT_HD void acs_stage(LaneState<MET>& s, const Operands& ops) {
-    using C = Core<MET, IN>;
-    constexpr int KIND = stage_kind<MET>(P);
-    constexpr int BIT = stage_bit(P);
-    const uint32_t one = ops.one;
-    if constexpr (KIND == KIND_HALF) {
-        // packed cores, phase 0: the two predecessors are the two halves of the same register
-#define VIT_HALF(r)                                                                               \
-    {                                                                                             \
-        uint32_t sw = prmt(s.pm[r], 0, 0x1032);                                                   \
-        uint32_t oc = cand<C, bm_type(r, P), false>(s.pm[r], ops);                                \
-        uint32_t pc = cand<C, bm_type(r, P), true>(sw, ops);                                      \
-        const uint32_t a = s.pp[r], b = s.pp[r + 4];                                              \
-        s.pm[r] = C::acs_sel(pc, oc, a, b, b, a, s.pp[r], s.pp[r + 4], false);                    \
-    }
-        VIT_HALF(0) VIT_HALF(1) VIT_HALF(2) VIT_HALF(3)
-#undef VIT_HALF
-    } else {
-        // register-local butterfly on register-index bit BIT: the even register's survivors use the SEL
-        // form (new registers), the odd register's the in-place predicated form
-        if constexpr (C::PACKED) {
-#define VIT_REG_PACKED(ra)                                                                        \
-    if constexpr (((ra >> BIT) & 1) == 0) {                                                       \
-        constexpr int rb = ra | (1 << BIT);                                                       \
-        const uint32_t ea = s.pm[ra], eb = s.pm[rb];                                              \
-        const uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb], pa1 = s.pp[ra + 4], pb1 = s.pp[rb + 4];    \
-        s.pm[ra] = C::acs_sel(cand<C, bm_type(ra, P), true>(eb, ops), cand<C, bm_type(ra, P), false>(ea, ops), \
-                              pa0, pb0, pa1, pb1, s.pp[ra], s.pp[ra + 4], false);                 \
-        s.pm[rb] = C::acs_mov(cand<C, bm_type(rb, P), true>(ea, ops), cand<C, bm_type(rb, P), false>(eb, ops), \
-                              s.pp[rb], pa0, s.pp[rb + 4], pa1, one, false);                      \
-    }
-            VIT_REG_PACKED(0) VIT_REG_PACKED(1) VIT_REG_PACKED(2) VIT_REG_PACKED(3)
-#undef VIT_REG_PACKED
-        } else {
-            // reference int32 core, phase 0: the odd predecessor wins ties for both new states
-            // (viterbiACS.cuh:136-142); all other phases: partner wins ties (viterbiACS.cuh:238-245)
-            constexpr bool ODD_WINS = (P == 0);
-#define VIT_REG_B32(ra)                                                                           \
-    if constexpr (((ra >> BIT) & 1) == 0) {                                                       \
-        constexpr int rb = ra | (1 << BIT);                                                       \
-        const uint32_t ea = s.pm[ra], eb = s.pm[rb];                                              \
-        const uint32_t pa0 = s.pp[ra], pb0 = s.pp[rb];                                            \
-        s.pm[ra] = C::template acs1_sel<false>(eb, opnd<bm_type(ra, P), true>(ops), ea, opnd<bm_type(ra, P), false>(ops), \
-                                               pa0, pb0, s.pp[ra], one);                          \
-        s.pm[rb] = C::template acs1_mov<ODD_WINS>(ea, opnd<bm_type(rb, P), true>(ops), eb, opnd<bm_type(rb, P), false>(ops), \
-                                                  s.pp[rb], pa0, one);                            \
-    }
-            VIT_REG_B32(0) VIT_REG_B32(1) VIT_REG_B32(2) VIT_REG_B32(3)
-            VIT_REG_B32(4) VIT_REG_B32(5) VIT_REG_B32(6) VIT_REG_B32(7)
-#undef VIT_REG_B32
-        }
-    }
-}
-
 // pp | (lf ^ SF), or lf ^ SF when ASSIGN: one LOP3 with an immediate.  Written as PTX so that the loop-invariant
 // (lf ^ SF) is not hoisted into a register per (register, batch) pair -- that costs ~90 registers.
 template <bool ASSIGN, uint32_t SF>
@@ -609,52 +445,9 @@ VIT_HD uint32_t or_xor(uint32_t pp, uint32_t lf) {
 #endif
 }
 
-// OR the survivors' newest message bits (== state index bits) into the register-exchange words.
-// NB bits (6 or 2) taken from the top of the 6-bit field, placed at bit SHIFT.
-template <int MET, int P, int SHIFT, int NB, bool ASSIGN>
-VIT_HD void insert_field(LaneState<MET>& s, uint32_t lane_field) {
-    const uint32_t lf = (NB == 6 ? lane_field : (lane_field >> 4)) << SHIFT;
-#define VIT_INS(k)                                                                                \
-    {                                                                                             \
-        constexpr uint32_t sf = (uint32_t)(NB == 6 ? static_field(k, P) : (static_field(k, P) >> 4)) << SHIFT; \
-        s.pp[k] = or_xor<ASSIGN, sf>(s.pp[k], lf);                                                \
-    }
-    VIT_INS(0) VIT_INS(1) VIT_INS(2) VIT_INS(3) VIT_INS(4) VIT_INS(5) VIT_INS(6) VIT_INS(7)
-#undef VIT_INS
-}
-
-// position index (lane*8 + reg) of the position that holds state `st` after the stage of phase p
-VIT_HD int pos_index_of_state(int st, int p) {
-    int v = 0;
-    for (int i = 0; i < 6; i++)
-        if ((st >> i) & 1) v ^= dual_of_slot(mod6(p + 1 + i), cum_of(p));
-    return (v & 7) * 8 + (v >> 3);
-}
-
-// the lane's part of the survivor field after the stage of phase p (XOR-ed with static_field)
-VIT_HD uint32_t lane_field_of(int l, int p) {
-    uint32_t f = 0;
-    for (int i = 0; i < 6; i++)
-        if (par3(l & f_after(p, i) & 7)) f |= 1u << (5 - i);
-    return f;
-}
-// the lane's part of the own-branch symbol entering stage p: operand class = 2*c0 + c1
-VIT_HD int lane_class_of(int l, int p) {
-    return par3(l & sym_func(0, p) & 7) * 2 + par3(l & sym_func(1, p) & 7);
-}
-
-// Half exchange before the stages of phases 2..5: the r0=1 registers (metrics and survivors) swap with lane ^ XM.
-template <int MET, int XM>
-VIT_HD void exchange_half(LaneState<MET>& s) {
-#pragma unroll
-    for (int r = 1; r < LaneState<MET>::NPM; r += 2) s.pm[r] = shfl_xor(s.pm[r], XM);
-#pragma unroll
-    for (int k = 1; k < 8; k += 2) s.pp[k] = shfl_xor(s.pp[k], XM);
-}
-
 // ------------------------------------------------------------------------------------------------
-// branch-metric table build: lane j of the group unpacks stage base+P+6j (P static) and writes the
-// four lane-class entries {W0,W1} for it.
+// branch-metric table build: one lane unpacks one stage and writes the four lane-class entries {W0,W1} for it
+// (HV = how the high half of a packed operand differs from the low half at that stage's phase, see half_variant)
 // ------------------------------------------------------------------------------------------------
 template <int MET, int IN>
 VIT_HD void load_symbols(const uint8_t* raw, int rel_stage, int& d0, int& d1, float& f0, float& f1) {
@@ -688,7 +481,7 @@ VIT_HD void load_symbols(const uint8_t* raw, int rel_stage, int& d0, int& d1, fl
     }
 }
 
-template <int MET, int IN, int P>
+template <int MET, int IN, int HV>
 VIT_HD void build_step(const uint8_t* raw, int rel_stage, uint32_t* entry /* 8 words: class-major */) {
     using C = Core<MET, IN>;
     int d0, d1; float f0, f1;
@@ -705,7 +498,6 @@ VIT_HD void build_step(const uint8_t* raw, int rel_stage, uint32_t* entry /* 8 w
     //   cl 3: ( A,  B)   cl 2: ( B,  A)   cl 1: (-B, -A)   cl 0: (-A, -B)
     const int X[4] = {-A, -B, B, A};
     const int Y[4] = {-B, -A, A, B};
-    constexpr int HV = half_variant(P);
 #pragma unroll
     for (int cl = 0; cl < 4; cl++) {
         uint32_t w0, w1;
@@ -722,233 +514,6 @@ VIT_HD void build_step(const uint8_t* raw, int rel_stage, uint32_t* entry /* 8 w
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// the warp body
-// ------------------------------------------------------------------------------------------------
-template <int MET, int IN, int BPP, int TBL>
-struct WarpCtx {
-    LaneState<MET> st;
-    uint8_t* smem;
-    int lane, g, l;
-    uint32_t one;
-    uint32_t bm_off[6];        // byte offset of this lane's class entry within a stage row, per phase
-    uint32_t bm_offn[6];       // ... and of the complementary class (3 - class): the same operands negated
-    uint32_t lane_field[3];    // phases 1,3,5
-    // segment geometry
-    unsigned long long seg_byte0;   // byte offset of the segment's first stage in the stream
-    const uint8_t* in;
-    uint8_t* out;
-    unsigned long long in_bytes;
-    unsigned long long out_word0;   // first decoded pack of this segment
-    unsigned seg_bits;              // L
-    unsigned t0;                    // absolute stage index of the current superchunk's stage 0
-};
-
-template <int MET, int IN, int BPP, int TBL>
-VIT_HD void issue_raw_copy(WarpCtx<MET, IN, BPP, TBL>& c, unsigned super_idx) {
-    using S = Smem<IN, TBL>;
-    constexpr int B96 = InTraits<IN>::B96;
-    unsigned long long b0 = c.seg_byte0 + (unsigned long long)super_idx * B96;
-    unsigned long long al = b0 & ~15ull;
-    uint8_t* dst = c.smem + S::OFF_RAW + c.g * S::RAW_SEG;
-#pragma unroll
-    for (int i = 0; i < (raw_pieces<IN>() + 7) / 8; i++) {
-        int piece = c.l + 8 * i;
-        if (piece < raw_pieces<IN>()) {
-            unsigned long long off = al + 16ull * piece;
-            unsigned valid = off >= c.in_bytes ? 0u : (c.in_bytes - off >= 16 ? 16u : (unsigned)(c.in_bytes - off));
-            const uint8_t* src = c.in + (valid ? off : 0);
-            cp_async16(dst + 16 * piece, src, valid);
-        }
-    }
-    cp_async_commit();
-}
-
-VIT_HD void store_row(uint32_t* row, const uint32_t (&e)[8]) {
-#if defined(__CUDA_ARCH__)
-    reinterpret_cast<uint4*>(row)[0] = make_uint4(e[0], e[1], e[2], e[3]);
-    reinterpret_cast<uint4*>(row)[1] = make_uint4(e[4], e[5], e[6], e[7]);
-#else
-    for (int i = 0; i < 8; i++) row[i] = e[i];
-#endif
-}
-
-// lane l of the group builds the rows of stages P + 6*(l + 8*round): j-block l + 8*round, row P
-template <int MET, int IN, int BPP, int TBL, int P>
-VIT_HD void build_phase(WarpCtx<MET, IN, BPP, TBL>& c, int round, unsigned skew) {
-    using S = Smem<IN, TBL>;
-    const uint8_t* raw = c.smem + S::OFF_RAW + c.g * S::RAW_SEG + skew;
-    const int j = c.l + 8 * round;
-    uint32_t e[8];
-    build_step<MET, IN, P>(raw, P + 6 * j, e);
-    uint32_t* row = reinterpret_cast<uint32_t*>(c.smem + S::OFF_BM + j * BM_JBLOCK + P * BM_ROW + c.g * 32);
-    store_row(row, e);
-}
-
-template <int MET, int IN, int BPP, int TBL>
-VIT_HD void build_table(WarpCtx<MET, IN, BPP, TBL>& c, unsigned skew) {
-#pragma unroll 1
-    for (int round = 0; round < 2; round++) {
-        build_phase<MET, IN, BPP, TBL, 0>(c, round, skew);
-        build_phase<MET, IN, BPP, TBL, 1>(c, round, skew);
-        build_phase<MET, IN, BPP, TBL, 2>(c, round, skew);
-        build_phase<MET, IN, BPP, TBL, 3>(c, round, skew);
-        build_phase<MET, IN, BPP, TBL, 4>(c, round, skew);
-        build_phase<MET, IN, BPP, TBL, 5>(c, round, skew);
-    }
-}
-
-// TBL == 32: the rows of slide W (stages 32W .. 32W+31) are built just before it runs.  Lane l builds stage
-// 32W + 6l + r in step r (phase (32W + r) % 6 is static per step), i.e. j-block l, row r; lanes 6,7 idle.
-template <int MET, int IN, int BPP, int TBL, int W>
-VIT_HD void build_slide(WarpCtx<MET, IN, BPP, TBL>& c, unsigned skew) {
-    using S = Smem<IN, TBL>;
-    const uint8_t* raw = c.smem + S::OFF_RAW + c.g * S::RAW_SEG + skew;
-    int l = c.l;
-#if defined(__CUDA_ARCH__)
-    // opaque copy of the lane index: the per-row shift amounts and offsets derived from it are loop invariant, and
-    // hoisting all 18 sets of them out of the super-step loop costs ~50 registers (occupancy is the point of TBL=32)
-    asm volatile("" : "+r"(l));
-#endif
-    uint8_t* blk = c.smem + S::OFF_BM + l * BM_JBLOCK + c.g * 32;
-#define VIT_BUILD_ROW(r)                                                                          \
-    if (6 * l + r < 32) {                                                                         \
-        uint32_t e[8];                                                                            \
-        build_step<MET, IN, (32 * W + r) % 6>(raw, 32 * W + 6 * l + r, e);                        \
-        uint32_t* row = reinterpret_cast<uint32_t*>(blk + r * BM_ROW);                            \
-        store_row(row, e);                                                                        \
-    }
-    VIT_BUILD_ROW(0) VIT_BUILD_ROW(1) VIT_BUILD_ROW(2) VIT_BUILD_ROW(3) VIT_BUILD_ROW(4) VIT_BUILD_ROW(5)
-#undef VIT_BUILD_ROW
-    syncwarp();
-}
-
-// subtract the segment-wide minimum metric (a common offset never changes a decision; the
-// reference does the same on a threshold, viterbiACS.cuh:307-378)
-template <int MET, int IN>
-VIT_HD void normalize(LaneState<MET>& s) {
-    using C = Core<MET, IN>;
-    uint32_t m = s.pm[0];
-#pragma unroll
-    for (int r = 1; r < LaneState<MET>::NPM; r++) m = C::vmin(m, s.pm[r]);
-    if constexpr (C::PACKED) m = C::vmin(m, prmt(m, 0, 0x1032));
-    m = C::vmin(m, shfl_xor(m, 1));
-    m = C::vmin(m, shfl_xor(m, 2));
-    m = C::vmin(m, shfl_xor(m, 4));
-#pragma unroll
-    for (int r = 0; r < LaneState<MET>::NPM; r++) s.pm[r] = C::sub(s.pm[r], m);
-}
-
-// stages per normalization: 96 (super-step start), 32 (slide end) or 16 (slide end and after its third loop iteration).
-// int16x2: offsets grow a metric by <= 2*offset per stage and it must stay below 2^15; half2: below 2048 (exact integers):
-// hard 2*96 + 12, s4/fp32 32*32 + 192, s8/s16 (5-bit symbols, offset 32) 64*18 + 384.
-template <int MET, int IN> constexpr int norm_period() {
-    return (MET == MET_B16) ? (IN == IN_S8 ? 32 : 96)
-         : (MET == MET_F16) ? (IN == IN_HARD ? 96 : (IN == IN_S8 || IN == IN_S16) ? 16 : 32)
-         : 96;
-}
-
-// End of a 32-stage slide (superchunk stage S = 32*SLOT + 31, phase P = S % 6): flush the
-// register-exchange words to ring slot SLOT, trace back from state 0, emit 32 decoded bits, start
-// the next survivor word.
-template <int MET, int IN, int BPP, int TBL, int SLOT>
-VIT_HD void slide_end(WarpCtx<MET, IN, BPP, TBL>& c) {
-    using SM = Smem<IN, TBL>;
-    constexpr int S = 32 * SLOT + 31;
-    constexpr int P = S % 6;                      // 1, 3, 5 for slots 0, 1, 2
-    uint8_t* ringb = c.smem + SM::OFF_RING;
-    uint32_t* mine = reinterpret_cast<uint32_t*>(ringb + (SLOT * SEGS_PER_WARP + c.g) * RING_SEG) + ring_word_of(c.l, 0);
-#if defined(__CUDA_ARCH__)
-    reinterpret_cast<uint4*>(mine)[0] = make_uint4(c.st.pp[0], c.st.pp[1], c.st.pp[2], c.st.pp[3]);
-    reinterpret_cast<uint4*>(mine)[1] = make_uint4(c.st.pp[4], c.st.pp[5], c.st.pp[6], c.st.pp[7]);
-#else
-    for (int k = 0; k < 8; k++) mine[k] = c.st.pp[k];
-#endif
-    // state 0 sits at position 0 in every phase: lane 0 of the group, register 0
-    uint32_t w_e = shfl_idx(c.st.pp[0], c.g * 8);
-    syncwarp();
-    const unsigned e = c.t0 + S;
-    if (e >= 95) {
-        unsigned st1 = brev32(w_e) & 63u;                                   // reference viterbiTB.cuh:9-12
-        const uint8_t* lut = c.smem + SM::OFF_LUT + SLOT * 64;             // word at e-32 has phase (P+4)%6
-        unsigned idx = lut[st1];
-        const uint32_t* prev = reinterpret_cast<const uint32_t*>(ringb + (((SLOT + 2) % 3) * SEGS_PER_WARP + c.g) * RING_SEG);
-        uint32_t word = prev[idx];                                          // viterbiTB.cuh:14-19
-        unsigned k = (e - 95) / 32;                                         // slide index
-        if (c.l == 0) {
-            if constexpr (BPP == 32) {
-                if (k * 32 < c.seg_bits) reinterpret_cast<uint32_t*>(c.out)[c.out_word0 + k] = word;
-            } else {
-                uint16_t* o = reinterpret_cast<uint16_t*>(c.out) + c.out_word0 + 2ull * k;
-                if (k * 32 < c.seg_bits) o[0] = (uint16_t)(word >> 16);
-                if (k * 32 + 16 < c.seg_bits) o[1] = (uint16_t)(word & 0xffff);
-            }
-        }
-    }
-    // start the next word: message bits e-5..e are the state index
-    insert_field<MET, P, 26, 6, true>(c.st, c.lane_field[P / 2]);
-    if constexpr (norm_period<MET, IN>() <= 32) normalize<MET, IN>(c.st);
-}
-
-// i-th insertion batch of a survivor word (i = 0..4), all at phase P: 6 bits at 20,14,8,2, then 2 bits at 0
-template <int MET, int P>
-VIT_HD void insert_batch(LaneState<MET>& st, uint32_t lane_field, int i) {
-    switch (i) {
-        case 0: insert_field<MET, P, 20, 6, false>(st, lane_field); break;
-        case 1: insert_field<MET, P, 14, 6, false>(st, lane_field); break;
-        case 2: insert_field<MET, P, 8, 6, false>(st, lane_field); break;
-        case 3: insert_field<MET, P, 2, 6, false>(st, lane_field); break;
-        default: insert_field<MET, P, 0, 2, false>(st, lane_field); break;
-    }
-}
-
-// stage S of the super-step; tbl = table base advanced by the loop iteration (i * BM_JBLOCK)
-template <int MET, int IN, int BPP, int TBL, int S>
-VIT_HD void one_stage(WarpCtx<MET, IN, BPP, TBL>& c, const uint8_t* tbl) {
-    constexpr int P = S % 6;
-    // class c holds (X, Y) in the core's operand encoding; class 3-c holds exactly (-X, -Y), so the
-    // operands of the opposite branches cost a second LDS.64 instead of arithmetic
-    const uint32_t* ent = reinterpret_cast<const uint32_t*>(tbl + row_off<TBL>(S) + c.bm_off[P]);
-    const uint32_t* entn = reinterpret_cast<const uint32_t*>(tbl + row_off<TBL>(S) + c.bm_offn[P]);
-    if constexpr (xmask_of(P) != 0) exchange_half<MET, xmask_of(P)>(c.st);
-#if defined(__CUDA_ARCH__)
-    const uint2 w = *reinterpret_cast<const uint2*>(ent);
-    const uint2 n = *reinterpret_cast<const uint2*>(entn);
-    acs_stage<MET, IN, P>(c.st, Operands{w.x, w.y, n.x, n.y, c.one});
-#else
-    acs_stage<MET, IN, P>(c.st, Operands{ent[0], ent[1], entn[0], entn[1], c.one});
-#endif
-}
-
-// One 32-stage slide = survivor word W of the super-step (stages 32W .. 32W+31):
-//   5 x { 6 stages ; insertion batch i }   (batches land on stages 32W+5, +11, +17, +23, +29)
-//   2 stages ; flush + traceback + emit     (stage 32W+31)
-// One loop branch and one batch dispatch per 6 stages; everything else is straight-line.
-// Returns true when the segment group has emitted its last word.
-template <int MET, int IN, int BPP, int TBL, int W>
-VIT_HD bool slide(WarpCtx<MET, IN, BPP, TBL>& c, unsigned Tmax) {
-    using SM = Smem<IN, TBL>;
-    constexpr int S0 = 32 * W;
-    constexpr int PB = (S0 + 5) % 6;              // phase of the batch stages: 5, 1, 3
-    const uint8_t* tbl = c.smem + SM::OFF_BM;
-#pragma unroll 1
-    for (int i = 0; i < 5; i++, tbl += BM_JBLOCK) {
-        one_stage<MET, IN, BPP, TBL, S0 + 0>(c, tbl);
-        one_stage<MET, IN, BPP, TBL, S0 + 1>(c, tbl);
-        one_stage<MET, IN, BPP, TBL, S0 + 2>(c, tbl);
-        one_stage<MET, IN, BPP, TBL, S0 + 3>(c, tbl);
-        one_stage<MET, IN, BPP, TBL, S0 + 4>(c, tbl);
-        one_stage<MET, IN, BPP, TBL, S0 + 5>(c, tbl);
-        insert_batch<MET, PB>(c.st, c.lane_field[PB / 2], i);
-        if constexpr (norm_period<MET, IN>() == 16) {
-            if (i == 2) normalize<MET, IN>(c.st);
-        }
-    }
-    one_stage<MET, IN, BPP, TBL, S0 + 30>(c, c.smem + SM::OFF_BM);
-    one_stage<MET, IN, BPP, TBL, S0 + 31>(c, c.smem + SM::OFF_BM);
-    slide_end<MET, IN, BPP, TBL, W>(c);
-    return c.t0 + 32 * (W + 1) >= Tmax;
-}
 
 // kp.gate_super[i] without dynamic indexing of the kernel parameters (that would copy them to local memory)
 VIT_HD unsigned gate_super_at(const KParams& kp, unsigned i) {
@@ -958,108 +523,25 @@ VIT_HD unsigned gate_super_at(const KParams& kp, unsigned i) {
     return v;
 }
 
-// Decode the 4 segments owned by warp `warp_id` of stream `stream`.
-template <int MET, int IN, int BPP, int TBL = 96>
-VIT_HD void warp_body(const KParams& kp, unsigned warp_id, unsigned stream, int lane, uint8_t* smem) {
-    using SM = Smem<IN, TBL>;
-    WarpCtx<MET, IN, BPP, TBL> c;
-    c.smem = smem; c.lane = lane; c.g = lane >> 3; c.l = lane & 7;
-    c.one = kp.one;
-
-    // segment partition, reference viterbi.cu:156-165
-    const unsigned W = kp.segments;
-    const unsigned long long q = kp.packs / W, rem = kp.packs % W;
-    const unsigned long long w = (unsigned long long)kp.seg_first + (unsigned long long)warp_id * SEGS_PER_WARP + c.g;
-    unsigned long long Lp = (w < kp.seg_limit) ? q + (w < rem ? 1 : 0) : 0;
-    const unsigned long long start_pack = q * w + (w < rem ? w : rem);
-    c.seg_bits = (unsigned)(Lp * BPP);
-    c.out_word0 = start_pack;
-    const unsigned long long s0 = start_pack * BPP;                       // first message index
-    c.seg_byte0 = s0 * InTraits<IN>::B96 / 96;
-    c.in = kp.in + (unsigned long long)stream * kp.in_stride;
-    c.out = kp.out + (unsigned long long)stream * kp.out_stride;
-    c.in_bytes = kp.in_bytes;
-
-    // the first segment of the warp is never shorter than the others
-    const unsigned long long w_first = (unsigned long long)kp.seg_first + (unsigned long long)warp_id * SEGS_PER_WARP;
-    const unsigned long long Lp_first = (w_first < kp.seg_limit) ? q + (w_first < rem ? 1 : 0) : 0;
-    if (Lp_first == 0) return;
-    const unsigned Lmax = (unsigned)(Lp_first * BPP);
-    const unsigned Tmax = 64 + 32 * ((Lmax + 31) / 32);                   // viterbi.cu:176-197
-    const unsigned nsuper = (Tmax + SUPER - 1) / SUPER;
-
-#pragma unroll
-    for (int p = 0; p < 6; p++) {
-        c.bm_off[p] = (uint32_t)(c.g * 32 + lane_class_of(c.l, p) * 8);
-        c.bm_offn[p] = (uint32_t)(c.g * 32 + (3 - lane_class_of(c.l, p)) * 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 3; i++) c.lane_field[i] = lane_field_of(c.l, 2 * i + 1);
-#pragma unroll
-    for (int r = 0; r < LaneState<MET>::NPM; r++) c.st.pm[r] = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) c.st.pp[k] = 0;
-
-    // traceback lookup: variant v (ring slot of e) -> ring word of a state at the phase of stage e-32
-    {
-        uint8_t* lut = smem + SM::OFF_LUT;
-        for (int i = lane; i < 3 * 64; i += 32) {
-            int v = i / 64, st = i % 64;
-            int pw = mod6((v * 32 + 31) + 4);                           // phase of stage e-32
-            int pos = pos_index_of_state(st, pw);                       // lane*8 + reg
-            lut[i] = (uint8_t)ring_word_of(pos >> 3, pos & 7);
-        }
-    }
-
-    // upload gates passed so far (uniform across the warp)
-    unsigned gate_next = 0;
-#define VIT_GATE(x)                                                                               \
-    while (gate_next < kp.gate_n && (x) >= gate_super_at(kp, gate_next)) {                        \
-        if (!gate_spin(kp.gate + gate_next, kp.gate_epoch)) { *kp.gate_err = 1u; return; }        \
-        gate_next++;                                                                              \
-    }
-    VIT_GATE(0u)
-    issue_raw_copy(c, 0);
-#pragma unroll 1
-    for (unsigned sc = 0; sc < nsuper; sc++) {
-        c.t0 = sc * SUPER;
-        const unsigned skew = (unsigned)((c.seg_byte0 + (unsigned long long)sc * InTraits<IN>::B96) & 15ull);
-        cp_async_wait<0>();
-        syncwarp();
-        // the raw staging buffer is single: the next super-step's words are requested as soon as the last table
-        // build of this one has consumed it, and land while the remaining stages run
-#define VIT_PREFETCH                                                                              \
-    if (sc + 1 < nsuper) {                                                                        \
-        VIT_GATE(sc + 1)                                                                          \
-        issue_raw_copy(c, sc + 1);                                                                \
-    }
-        if constexpr (TBL == 96) {
-            build_table(c, skew);
-            syncwarp();
-            VIT_PREFETCH
-        }
-        if constexpr (norm_period<MET, IN>() == 96) normalize<MET, IN>(c.st);
-        if constexpr (TBL == 32) build_slide<MET, IN, BPP, TBL, 0>(c, skew);
-        if (slide<MET, IN, BPP, TBL, 0>(c, Tmax)) break;
-        if constexpr (TBL == 32) build_slide<MET, IN, BPP, TBL, 1>(c, skew);
-        if (slide<MET, IN, BPP, TBL, 1>(c, Tmax)) break;
-        if constexpr (TBL == 32) {
-            build_slide<MET, IN, BPP, TBL, 2>(c, skew);
-            VIT_PREFETCH
-        }
-        if (slide<MET, IN, BPP, TBL, 2>(c, Tmax)) break;
-        syncwarp();
-    }
-#undef VIT_PREFETCH
-#undef VIT_GATE
-}
-
-#if defined(__CUDACC__)
-template <int MET, int IN, int BPP, int TBL>
-__global__ void __launch_bounds__(32) vit_decode_kernel(const KParams kp) {
-    extern __shared__ __align__(16) uint8_t vit_smem[];
-    warp_body<MET, IN, BPP, TBL>(kp, blockIdx.x, blockIdx.y, (int)threadIdx.x, vit_smem);
-}
-#endif
+// ------------------------------------------------------------------------------------------------
+// The decoder proper (state map, shared-memory layout, stage code, warp body, kernel) is written once in
+// vit_kernel_map.inc for a lane geometry given by VIT_NLB (lane bits per segment):
+//   vitk::l8  8 lanes per segment, 4 segments per warp, 8 states per lane  -- the product kernels;
+//   vitk::l4  4 lanes per segment, 8 segments per warp, 16 states per lane -- 3 half exchanges per 6 stages instead of 4,
+//             10 % fewer instructions per decoded bit, but half as many warps: measured slower, so the library
+//             does not instantiate its kernels.  The host emulator runs both (tests/test_emu_kernel.py): the map algebra
+//             is the same code.
+// ------------------------------------------------------------------------------------------------
+#define VIT_NLB 3
+namespace l8 {
+#include "vit_kernel_map.inc"
+}  // namespace l8
+#undef VIT_NLB
+#define VIT_NLB 2
+namespace l4 {
+#include "vit_kernel_map.inc"
+}  // namespace l4
+#undef VIT_NLB
 
 }  // namespace vitk
+

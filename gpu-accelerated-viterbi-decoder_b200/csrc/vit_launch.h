@@ -5,7 +5,8 @@
 
 namespace vitk {
 struct KernelEntry {
-    cudaError_t (*launch)(const KParams& kp, dim3 grid, cudaStream_t stream);
+    // decodes segments [kp.seg_first, kp.seg_limit) of kp.nstreams streams; picks the kernel build and the grid itself
+    cudaError_t (*launch)(const KParams& kp, cudaStream_t stream);
     const void* func;
     int smem_bytes;
 };

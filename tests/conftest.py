@@ -35,7 +35,7 @@ def emu():
     import ctypes as C
     d = os.path.join(ROOT, "tests", "emu")
     so = os.path.join(d, "libvitemu.so")
-    srcs = [os.path.join(d, "vit_emu.cpp"), os.path.join(PKG_DIR, "csrc", "vit_kernel.cuh")]
+    srcs = [os.path.join(d, "vit_emu.cpp"), os.path.join(PKG_DIR, "csrc", "vit_kernel.cuh"), os.path.join(PKG_DIR, "csrc", "vit_kernel_map.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([gxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, srcs[0]])

@@ -55,6 +55,25 @@ def test_kernel_source_small_table_variant(emu, O, opt):
         emu.vit_emu_set_table(96)
 
 
+@pytest.mark.parametrize("tbl", [96, 32])
+@pytest.mark.parametrize("opt", ALL_OPTS)
+def test_kernel_source_four_lane_geometry(emu, O, opt, tbl):
+    """The l4 instantiation of the kernel (4 lanes per segment, 8 segments per warp, 16 states per lane, three half
+    exchanges per 6 stages; used for multi-stream launches) decodes the same words."""
+    emu.vit_emu_set_lanes(4)
+    emu.vit_emu_set_table(tbl)
+    try:
+        run_case(emu, O, opt, 3000 + 64 + 7, 12, seed=5, sigma=0.9)
+        run_case(emu, O, opt, 1500 + 64, 5, seed=1, zero=True)
+        run_case(emu, O, opt, 64 + 32 * 3 + 16, 8, seed=9, sigma=0.5)
+        if tbl == 32:
+            amp = {0: 64, 1: 7, 2: 127, 3: 32767, 4: 128}[opt & 0xF]
+            run_case(emu, O, opt, 12000 + 64, 4, seed=11, sigma=1.0, amp=amp)
+    finally:
+        emu.vit_emu_set_lanes(8)
+        emu.vit_emu_set_table(96)
+
+
 @pytest.mark.parametrize("opt", [0x012, 0x112, 0x011, 0x024, 0x022, 0x003])
 def test_kernel_source_long_segments(emu, O, opt):
     """Several 96-stage super-steps per segment, saturated symbols: exercises the metric range
