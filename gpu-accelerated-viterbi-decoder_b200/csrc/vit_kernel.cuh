@@ -528,9 +528,11 @@ VIT_HD unsigned gate_super_at(const KParams& kp, unsigned i) {
 // vit_kernel_map.inc for a lane geometry given by VIT_NLB (lane bits per segment):
 //   vitk::l8  8 lanes per segment, 4 segments per warp, 8 states per lane  -- the product kernels;
 //   vitk::l4  4 lanes per segment, 8 segments per warp, 16 states per lane -- 3 half exchanges per 6 stages instead of 4,
-//             10 % fewer instructions per decoded bit, but half as many warps: measured slower, so the library
-//             does not instantiate its kernels.  The host emulator runs both (tests/test_emu_kernel.py): the map algebra
-//             is the same code.
+//             10 % fewer instructions per decoded bit, but half as many warps;
+//   vitk::l16 16 lanes per segment, 2 segments per warp, 4 states per lane -- twice as many warps, 5 half exchanges per 6
+//             stages, 17 % more instructions per decoded bit.
+// Both alternatives were measured slower than l8, so the library does not instantiate their kernels.  The
+// host emulator runs all three (tests/test_emu_kernel.py): the map algebra is the same code.
 // ------------------------------------------------------------------------------------------------
 #define VIT_NLB 3
 namespace l8 {
@@ -541,6 +543,11 @@ namespace l8 {
 namespace l4 {
 #include "vit_kernel_map.inc"
 }  // namespace l4
+#undef VIT_NLB
+#define VIT_NLB 4
+namespace l16 {
+#include "vit_kernel_map.inc"
+}  // namespace l16
 #undef VIT_NLB
 
 }  // namespace vitk

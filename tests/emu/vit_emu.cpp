@@ -61,7 +61,10 @@ Job g_job;
 
 template <int MET, int IN, int BPP>
 void run_lane(int lane) {
-    if (g_job.lanes == 4) {
+    if (g_job.lanes == 16) {
+        if (g_job.tbl == 32) vitk::l16::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
+        else vitk::l16::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
+    } else if (g_job.lanes == 4) {
         if (g_job.tbl == 32) vitk::l4::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
         else vitk::l4::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
     } else {
@@ -109,7 +112,7 @@ void run_warp() {
 }  // namespace
 
 extern "C" void vit_emu_set_table(int tbl) { g_job.tbl = tbl == 32 ? 32 : 96; }
-extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 4 ? 4 : 8; }
+extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 4 ? 4 : lanes == 16 ? 16 : 8; }
 
 extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inputNum, unsigned segments,
                               unsigned nstreams, size_t in_stride, size_t out_stride) {
@@ -126,7 +129,7 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     g_job.met = mt == 0 ? vitk::MET_B32 : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
     g_job.in = it; g_job.bpp = bpp;
     g_job.smem = (uint8_t*)aligned_alloc(128, 64 * 1024);
-    const unsigned spw = g_job.lanes == 4 ? 8 : 4;
+    const unsigned spw = 32 / g_job.lanes;
     unsigned nwarps = (segments + spw - 1) / spw;
     for (unsigned s = 0; s < nstreams; s++)
         for (unsigned w = 0; w < nwarps; w++) {

@@ -55,6 +55,20 @@ def test_kernel_source_small_table_variant(emu, O, opt):
         emu.vit_emu_set_table(96)
 
 
+@pytest.mark.parametrize("opt", [0x011, 0x000, 0x121, 0x112, 0x004, 0x023, 0x002])
+def test_kernel_source_sixteen_lane_geometry(emu, O, opt):
+    emu.vit_emu_set_lanes(16)
+    try:
+        for tbl in (96, 32):
+            emu.vit_emu_set_table(tbl)
+            run_case(emu, O, opt, 3000 + 64 + 7, 12, seed=5, sigma=0.9)
+            run_case(emu, O, opt, 1500 + 64, 5, seed=1, zero=True)
+            run_case(emu, O, opt, 64 + 32 * 3 + 16, 8, seed=9, sigma=0.5)
+    finally:
+        emu.vit_emu_set_lanes(8)
+        emu.vit_emu_set_table(96)
+
+
 @pytest.mark.parametrize("tbl", [96, 32])
 @pytest.mark.parametrize("opt", ALL_OPTS)
 def test_kernel_source_four_lane_geometry(emu, O, opt, tbl):
