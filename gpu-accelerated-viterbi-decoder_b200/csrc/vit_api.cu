@@ -225,8 +225,13 @@ int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
     GatePlan gp;
     // column blocks of 1/2, 3/8 and 1/8 of a segment (profiles/r1_upload_pattern_probe.txt): fewer, wider strided copies
     // upload faster (0.66 ms for 32 MB against 0.69 with four blocks), a short last block keeps the tail short
+    // That is for inputs whose upload takes longer than their decode (>= 1 byte per decoded bit at ~50 GB/s against
+    // 12-16 ps per bit).  Hard-decision input (0.25 byte per bit) is decode bound: a small first block lets the kernel start
+    // early and the rest arrives long before it is needed.
     gp.n = 3;
-    gp.super[0] = 0; gp.super[1] = (unsigned)(g.nsuper / 2); gp.super[2] = (unsigned)(g.nsuper * 7 / 8);
+    gp.super[0] = 0;
+    if (in_type(h->options) == 0) { gp.super[1] = (unsigned)(g.nsuper / 8); gp.super[2] = (unsigned)(g.nsuper / 2); }
+    else { gp.super[1] = (unsigned)(g.nsuper / 2); gp.super[2] = (unsigned)(g.nsuper * 7 / 8); }
     VIT_CUDA(cudaStreamSynchronize(h->stream));           // a kernel abandoned by a failed earlier call may still own the error word
     h->epoch_h[16] = 0;
     h->epoch++;
@@ -457,7 +462,7 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
     const HostRun hr = host_run_geometry(h, in_h, out_h, inputNum);
     // VIT_RUN_MODE=2 (measurement hook) forces the segment-range chunk pipeline where the time-sliced upload would be used
     static const int run_mode = [] { const char* e = getenv("VIT_RUN_MODE"); return e ? atoi(e) : 0; }();
-    if (kernel_ms || hr.nch < 2 || hr.W < 64) return run_sequential(h, hr, kernel_ms);
+    if (kernel_ms || hr.W < 64) return run_sequential(h, hr, kernel_ms);
     if (run_mode == 0 && gated_upload_applies(h, hr)) {
         bool gave_up = false;
         rc = run_gated(h, hr, &gave_up);
@@ -467,6 +472,7 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
         // the chunk pipeline and stop using gates on this handle.
         h->gates_disabled = true;
     }
+    if (hr.nch < 2) return run_sequential(h, hr, nullptr);
     return run_chunked(h, hr);
 }
 
