@@ -449,43 +449,55 @@ VIT_HD uint32_t or_xor(uint32_t pp, uint32_t lf) {
 // branch-metric table build: one lane unpacks one stage and writes the four lane-class entries {W0,W1} for it
 // (HV = how the high half of a packed operand differs from the low half at that stage's phase, see half_variant)
 // ------------------------------------------------------------------------------------------------
-template <int MET, int IN>
-VIT_HD void load_symbols(const uint8_t* raw, int rel_stage, int& d0, int& d1, float& f0, float& f1) {
+// the raw channel word(s) of one stage; loaded separately from their decoding so that a builder can issue all its loads
+// before its first table store (the compiler will not move a shared-memory load above a store it cannot disambiguate)
+struct RawSym { uint32_t w; float f0, f1; };
+template <int IN>
+VIT_HD RawSym load_raw(const uint8_t* raw, int rel_stage) {
     // raw points at the byte holding the first stage of this superchunk (word aligned)
+    RawSym r{0u, 0.f, 0.f};
+    if constexpr (IN == IN_HARD) r.w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 4));
+    else if constexpr (IN == IN_S4) r.w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 2));
+    else if constexpr (IN == IN_S8) r.w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 1));
+    else if constexpr (IN == IN_S16) r.w = *reinterpret_cast<const uint32_t*>(raw + 4 * rel_stage);
+    else {
+        const float* p = reinterpret_cast<const float*>(raw + 8 * rel_stage);
+        r.f0 = p[0]; r.f1 = p[1];
+    }
+    return r;
+}
+template <int MET, int IN>
+VIT_HD void decode_symbols(const RawSym& r, int rel_stage, int& d0, int& d1, float& f0, float& f1) {
     d0 = d1 = 0; f0 = f1 = 0.f;
+    const uint32_t w = r.w;
     if constexpr (IN == IN_HARD) {
         // 32 symbols per int32, MSB first (reference viterbiBM.cuh:33-40)
-        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 4));
         uint32_t rx = (w >> (30 - 2 * (rel_stage & 15))) & 3u;
         d0 = 2 * (int)(rx >> 1) - 1; d1 = 2 * (int)(rx & 1) - 1;   // +-1, halved after the sum
     } else if constexpr (IN == IN_S4) {
-        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 2));   // viterbiBM.cuh:64-75
-        int sh = 24 - 8 * (rel_stage & 3);
+        int sh = 24 - 8 * (rel_stage & 3);                          // viterbiBM.cuh:64-75
         d0 = ((int)(w << (24 - sh))) >> 28;
         d1 = ((int)(w << (28 - sh))) >> 28;
     } else if constexpr (IN == IN_S8) {
-        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * (rel_stage >> 1));   // viterbiBM.cuh:97-100
-        int sh = 16 - 16 * (rel_stage & 1);
+        int sh = 16 - 16 * (rel_stage & 1);                         // viterbiBM.cuh:97-100
         d0 = (int)(int8_t)(w >> (sh + 8));
         d1 = (int)(int8_t)(w >> sh);
         if constexpr (MET == MET_F16) { d0 >>= 3; d1 >>= 3; }       // extension: keep half2 exact
     } else if constexpr (IN == IN_S16) {
-        uint32_t w = *reinterpret_cast<const uint32_t*>(raw + 4 * rel_stage);          // viterbiBM.cuh:121-124
-        d0 = (int)(int16_t)(w >> 16);
+        d0 = (int)(int16_t)(w >> 16);                               // viterbiBM.cuh:121-124
         d1 = (int)(int16_t)(w & 0xffff);
         if constexpr (MET == MET_F16) { d0 >>= 11; d1 >>= 11; }
     } else {
-        const float* p = reinterpret_cast<const float*>(raw + 8 * rel_stage);          // viterbiBM.cuh:146-153
-        f0 = fminf(fmaxf(p[0], -8.0f), 7.0f);
-        f1 = fminf(fmaxf(p[1], -8.0f), 7.0f);
+        f0 = fminf(fmaxf(r.f0, -8.0f), 7.0f);                       // viterbiBM.cuh:146-153
+        f1 = fminf(fmaxf(r.f1, -8.0f), 7.0f);
     }
 }
 
 template <int MET, int IN, int HV>
-VIT_HD void build_step(const uint8_t* raw, int rel_stage, uint32_t* entry /* 8 words: class-major */) {
+VIT_HD void build_step(const RawSym& rs, int rel_stage, uint32_t* entry /* 8 words: class-major */) {
     using C = Core<MET, IN>;
     int d0, d1; float f0, f1;
-    load_symbols<MET, IN>(raw, rel_stage, d0, d1, f0, f1);
+    decode_symbols<MET, IN>(rs, rel_stage, d0, d1, f0, f1);
     int A, B;
     if constexpr (IN == IN_F32) {
         A = (int)(f0 + f1); B = (int)(f0 - f1);                     // truncation is odd-symmetric
