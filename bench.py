@@ -518,7 +518,7 @@ def main():
                          "peak_at_measured_clock": issue_peak_at_clock, "frac_at_measured_clock": k_gbps / issue_peak_at_clock,
                          "achieved_acs_warp_inst_per_s": k_gbps * 1e9 * wi_per_bit, "peak_warp_inst_per_s": N_SM * 4 * sm_max_mhz * 1e6,
                          "how": "ACS-op roofline: 192 add/compare-select ops per decoded bit = %d warp-instructions; peak = 148 SM x 4 issue/clk x f_SM / that" % wi_per_bit,
-                         "traffic": NCU_DRAM_BYTES.get((args.workload, S)), "traffic_source": "profiles/r1_v6_ncu_core_0x011.txt (dram__bytes_read+write per launch, one ncu --set full capture)" if NCU_DRAM_BYTES.get((args.workload, S)) else None},
+                         "traffic": NCU_DRAM_BYTES.get((args.workload, S)), "traffic_source": "profiles/r1_v7_ncu_core_0x011.txt (dram__bytes_read+write per launch, one ncu --set full capture)" if NCU_DRAM_BYTES.get((args.workload, S)) else None},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e6), "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (kernel_ms * 1e6) / hbm_peak, "peak_kind": peak_kind, "traffic": NCU_DRAM_BYTES.get((args.workload, S)),
                              "algorithmic_bytes_per_launch": alg_bytes},
