@@ -432,15 +432,18 @@ def main():
     launches0 = dec.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
-        # same kernels again, for at least 0.3 s: NVML answers a clock query in milliseconds to tens of milliseconds,
-        # so a short timed region alone may hold few samples; the sampler sees this identical load as well
-        k, t_load = 0, time.perf_counter()
-        while k < args.warmup or time.perf_counter() - t_load < 0.3:
+        # same kernels again, for about 0.3 s: NVML answers a clock query in milliseconds to tens of milliseconds,
+        # so a short timed region alone may hold few samples; the sampler sees this identical load as well.
+        # The step count is derived from the workload size only, NOT from a clock: every rank must run the same number
+        # of steps, because step() issues the NCCL gathers (a clock-driven loop count differs between ranks and
+        # desynchronises the collectives).
+        est_step_s = M * S / 80e9
+        n_load = max(args.warmup, min(2000, int(0.3 / est_step_s) + 1))
+        for k in range(n_load):
             step(k)
-            k += 1
-            if k % 64 == 0:
+            if (k + 1) % 64 == 0:
                 st.synchronize()
-        drain(k - 1)
+        drain(n_load - 1)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
