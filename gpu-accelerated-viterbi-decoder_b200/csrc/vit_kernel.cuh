@@ -26,7 +26,8 @@
 //   * Survivors: 32-bit register-exchange words moved with predicated selects (VIMNMX.S16x2 yields
 //     both decision predicates; the int32 core derives the decision from a fused VIADDMNMX).  The
 //     decision bits themselves are never shifted in one by one: the last 6 message bits of a survivor
-//     are its state index, so they are merged in as a 6-bit field (one LOP3) every 6 stages.
+//     are its state index, so every 6 stages each word is shifted left by 6 and its register's index field is added
+//     (one IMAD per word, the same code in every loop iteration).
 //   * The one-pointer ring (3 x 64 words per segment) lives in shared memory, not global.
 //   * Optional upload gates let one launch start before its input has arrived (vit_run's time-sliced copy-in).
 //
