@@ -25,6 +25,7 @@ CHANNEL_MASK, METRIC_MASK, DECODE_MASK, COMP_MASK = 0xF, 0xF0, 0xF00, 0xF000
 constLen, polyn1, polyn2 = 7, 0o171, 0o133
 extraL, extraR, slideSize, forwardLen = 26, 38, 32, 96
 SEGMENTS = 6400
+UPLOAD_AUTO, UPLOAD_SEQUENTIAL, UPLOAD_CHUNKED, UPLOAD_GATED = 0, 1, 2, 3
 
 
 class ViterbiError(RuntimeError):
@@ -69,6 +70,12 @@ def lib():
         L.vit_host_free.restype, L.vit_host_free.argtypes = None, [vp]
         L.vit_synth_device.restype = C.c_int
         L.vit_synth_device.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, vp, vp, vp]
+        L.vit_set_upload_mode.restype, L.vit_set_upload_mode.argtypes = C.c_int, [vp, C.c_int]
+        L.vit_upload_mode_in_effect.restype, L.vit_upload_mode_in_effect.argtypes = C.c_int, [vp]
+        L.vit_synth_device_ex.restype = C.c_int
+        L.vit_synth_device_ex.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp, vp]
+        L.vit_count_errors_synth_device.restype = C.c_int
+        L.vit_count_errors_synth_device.argtypes = [C.c_int, vp, sz, C.c_uint, C.c_int, C.POINTER(C.c_ulonglong), vp]
         _lib = L
     return _lib
 
@@ -96,11 +103,23 @@ def parse_options(input="h", metric="b32", output="b32", comp="reg"):
     return i | m | o | c
 
 
-def synth_device(input_type, n_bits, packed_ptr, bits_ptr=None, seed=1, amp=0, sigma=0.0, zero=False, stream=0):
-    """Device-side synthetic received stream (vit_synth_device): the GPU twin of the reference harness's host
-    source/encoder/noise/packer chain.  packed_ptr must hold whole 32-bit packs."""
-    _check(lib().vit_synth_device(int(input_type), int(n_bits), int(seed), int(amp), float(sigma), int(bool(zero)),
-                                  packed_ptr, bits_ptr, stream))
+SOURCE_HASH, SOURCE_PRBS31 = 0, 1
+
+
+def synth_device(input_type, n_bits, packed_ptr, bits_ptr=None, seed=1, amp=0, sigma=0.0, zero=False, stream=0,
+                 source=SOURCE_HASH):
+    """Device-side synthetic received stream (vit_synth_device_ex): the GPU twin of the reference harness's host
+    source/encoder/noise/packer chain.  packed_ptr must hold whole 32-bit packs.  source: counter-hash message bits or
+    PRBS-31 started from state `seed`."""
+    _check(lib().vit_synth_device_ex(int(input_type), int(n_bits), int(seed), int(amp), float(sigma), int(bool(zero)),
+                                     int(source), packed_ptr, bits_ptr, stream))
+
+
+def count_errors_synth_device(options, out_ptr, message_len, seed=1, source=SOURCE_HASH, stream=0):
+    """Bit errors against the synthetic source's own message bits, regenerated on the device (no bits buffer)."""
+    n = C.c_ulonglong(0)
+    _check(lib().vit_count_errors_synth_device(int(options), out_ptr, int(message_len), int(seed), int(source), C.byref(n), stream))
+    return int(n.value)
 
 
 def count_errors_device(options, out_ptr, bits_ptr, message_len, stream=0):
@@ -153,6 +172,10 @@ class ViterbiCUDA:
         nwords = self.getOutputSize(inputNum) // np.dtype(self.decPack_t).itemsize
         if output_h is None:
             output_h = np.empty(nwords, self.decPack_t)
+        elif (not isinstance(output_h, np.ndarray) or output_h.nbytes < self.getOutputSize(inputNum)
+              or not output_h.flags["C_CONTIGUOUS"] or not output_h.flags["WRITEABLE"]):
+            raise ViterbiError("output_h must be a writable C-contiguous numpy array of at least %d bytes"
+                               % self.getOutputSize(inputNum))
         ms = C.c_float(0)
         _check(lib().vit_run(self._h, input_h.ctypes.data, output_h.ctypes.data, inputNum,
                              C.byref(ms) if want_kernel_time else None))
@@ -165,6 +188,13 @@ class ViterbiCUDA:
         _check(lib().vit_run_device_batch(self._h, in_ptr, out_ptr, inputNum, nstreams, in_stride, out_stride,
                                           stream, C.byref(ms) if want_kernel_time else None))
         return ms.value if want_kernel_time else None
+
+    def set_upload_mode(self, mode):
+        """UPLOAD_AUTO / _SEQUENTIAL / _CHUNKED / _GATED: how run() moves host buffers (vit_set_upload_mode)."""
+        _check(lib().vit_set_upload_mode(self._h, int(mode)))
+
+    def upload_mode_in_effect(self):
+        return int(lib().vit_upload_mode_in_effect(self._h))
 
     def kernel_info(self):
         v = [C.c_int(0) for _ in range(4)]

@@ -11,12 +11,18 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "../../include/vit_b200.h"
 #include "vit_launch.h"
@@ -40,6 +46,94 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int EXTRA = 64;  // extraL + extraR, reference viterbi.h:70-76
+
+// The API calls run on the handle's device but leave the caller's current device as they found it (a multi-GPU
+// process that holds one handle per device must not have its thread's device changed under it).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev == device) return cudaSuccess;
+        switched = true;
+        return cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+};
+#define VIT_ON_DEVICE(h) DeviceGuard guard_; VIT_CUDA(guard_.enter((h)->device))
+
+// Worker threads that copy pageable host memory into the pinned staging buffers (vit_run with pageable buffers).
+// The workers sleep between calls and spin between the jobs of one call (a condition-variable wake-up per column block
+// would cost more than the block's copy).
+class StagePool {
+public:
+    explicit StagePool(int nthreads) {
+        for (int i = 0; i < nthreads; i++) th_.emplace_back([this] { worker(); });
+    }
+    ~StagePool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return (int)th_.size() + 1; }
+    void begin_call() {
+        { std::lock_guard<std::mutex> lk(m_); active_.store(true); }
+        cv_.notify_all();
+    }
+    void end_call() { active_.store(false); }
+    // fn(i) for i in [0, n); the caller takes part; returns when all items are done
+    void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+        if (n == 0) return;
+        fn_ = &fn; n_ = n;
+        done_.store(0, std::memory_order_relaxed);
+        const unsigned long long g = gen_.load(std::memory_order_relaxed) + 1;
+        next_.store(g << 32, std::memory_order_release);
+        gen_.store(g, std::memory_order_release);
+        drain(g);
+        while (done_.load(std::memory_order_acquire) < n) spin_pause();
+    }
+
+private:
+    static void spin_pause() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    void drain(unsigned long long g) {
+        for (;;) {
+            unsigned long long v = next_.load(std::memory_order_acquire);
+            if ((v >> 32) != g || (v & 0xffffffffull) >= n_) return;
+            if (!next_.compare_exchange_weak(v, v + 1, std::memory_order_acq_rel)) continue;
+            (*fn_)((size_t)(v & 0xffffffffull));
+            done_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void worker() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return stop_ || active_.load(); });
+                if (stop_) return;
+            }
+            for (;;) {
+                const unsigned long long g = gen_.load(std::memory_order_acquire);
+                if (g != seen) { seen = g; drain(g); continue; }
+                if (!active_.load(std::memory_order_acquire)) break;
+                for (int k = 0; k < 64 && gen_.load(std::memory_order_acquire) == seen; k++) spin_pause();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+    std::atomic<bool> active_{false};
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t n_ = 0;
+    std::atomic<unsigned long long> gen_{0}, next_{0};
+    std::atomic<size_t> done_{0};
+};
 
 inline int in_type(int o) { return o & 0xf; }
 inline int met_type(int o) { return (o >> 4) & 0xf; }
@@ -91,9 +185,19 @@ struct vit_handle {
     unsigned* gate_err_d = nullptr;      // device address of epoch_h[16] (mapped): set by a warp that gave up waiting
     unsigned epoch = 0;
     cudaEvent_t ev_kdone = nullptr;
-    // tools that inject into the CUDA driver (ncu, nsys, compute-sanitizer) may serialise kernels and copies: a
-    // kernel that waits for a copy issued after it would then never see it
-    bool gates_disabled = getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr;
+    // The time-sliced upload needs copies to make progress while a kernel that waits for them is running.  That is not
+    // the case when a tool injected into the CUDA driver serialises kernels and copies (ncu, nsys, compute-sanitizer),
+    // when every stream shares one hardware queue (CUDA_DEVICE_MAX_CONNECTIONS=1) or when launches block the host
+    // (CUDA_LAUNCH_BLOCKING=1): detected up front, vit_run then takes the segment-range chunk pipeline.
+    bool gates_disabled = env_forbids_gates();
+    int upload_mode = VIT_UPLOAD_AUTO;    // vit_set_upload_mode
+    unsigned long long gate_timeout_ns = 2000000000ull;
+    StagePool* pool = nullptr;            // created on the first vit_run with pageable buffers
+    static bool env_forbids_gates() {
+        auto is = [](const char* name, const char* v) { const char* e = getenv(name); return e && strcmp(e, v) == 0; };
+        return getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+               is("CUDA_DEVICE_MAX_CONNECTIONS", "1") || is("CUDA_LAUNCH_BLOCKING", "1");
+    }
 };
 
 namespace {
@@ -134,6 +238,7 @@ int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, 
     kp.nstreams = (unsigned)nstreams;
     kp.one = 1u;
     kp.gate = h->gate_d; kp.gate_err = h->gate_err_d; kp.gate_epoch = h->epoch; kp.gate_n = 0;
+    kp.gate_timeout_ns = h->gate_timeout_ns;
     for (int i = 0; i < 8; i++) kp.gate_super[i] = 0;
     if (gp && h->gate_d) {
         kp.gate_n = gp->n;
@@ -153,6 +258,9 @@ int launch(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t
     if (M == 0 || nstreams == 0) { if (kernel_ms) *kernel_ms = 0.f; return VIT_OK; }
     if ((reinterpret_cast<uintptr_t>(in_d) & 15) || (in_stride & 15))
         return fail(VIT_ERR_ARG, "device input must be 16-byte aligned (ptr %p, stride %zu)", in_d, in_stride);
+    const size_t pack_align = (size_t)bpp_of(o) / 8;
+    if ((reinterpret_cast<uintptr_t>(out_d) & (pack_align - 1)) || (out_stride & (pack_align - 1)))
+        return fail(VIT_ERR_ARG, "device output must be aligned to its %zu-byte packs (ptr %p, stride %zu)", pack_align, out_d, out_stride);
     if (nstreams > 65535) return fail(VIT_ERR_ARG, "at most 65535 streams per launch (got %zu)", nstreams);
     int rc = launch_range(h, in_d, out_d, inputNum, nstreams, in_stride, out_stride, st, 0, h->segments,
                           kernel_ms ? h->ev0 : nullptr, kernel_ms ? h->ev1 : nullptr);
@@ -215,27 +323,63 @@ bool is_pinned(const void* p) {
 }
 
 bool gated_upload_applies(const vit_handle* h, const HostRun& g) {
+    if (h->upload_mode == VIT_UPLOAD_GATED) return h->gate_d && h->gate_err_d && g.q >= 1 && g.nsuper >= 8;
     if (h->gates_disabled || !h->gate_d || !h->gate_err_d) return false;
     if (g.q < 1 || g.nsuper < 16 || g.in_bytes < (2u << 20)) return false;      // too short to be worth slicing
     return true;
 }
 
-// Time-sliced upload (pinned host input): ONE decode launch starts at once and every warp waits at "upload gates" for
-// the next column block of its segments; the copy stream uploads block b of EVERY segment (two strided copies: the
-// first P%W segments are one pack longer) and then opens gate b.  The decode therefore finishes one short block
-// after the last byte has landed, instead of a whole per-segment chain (0.25-0.4 ms) after it as with segment-range
-// chunks.  *gave_up is set when a warp stopped waiting for a gate (the output is then incomplete).
-int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
+int ensure_staging(vit_handle* h, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > h->pin_in_cap) {
+        delete h->pool;
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+        h->pin_in = nullptr; h->pin_in_cap = 0;
+        VIT_CUDA(cudaHostAlloc(&h->pin_in, in_bytes + 256, cudaHostAllocDefault));
+        h->pin_in_cap = in_bytes;
+    }
+    if (out_bytes > h->pin_out_cap) {
+        if (h->pin_out) cudaFreeHost(h->pin_out);
+        h->pin_out = nullptr; h->pin_out_cap = 0;
+        VIT_CUDA(cudaHostAlloc(&h->pin_out, out_bytes + 256, cudaHostAllocDefault));
+        h->pin_out_cap = out_bytes;
+    }
+    if (!h->pool) {
+        const char* e = getenv("VIT_STAGE_THREADS");
+        int n = e ? atoi(e) : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        n = std::max(1, std::min(n, 64));
+        h->pool = new (std::nothrow) StagePool(n - 1);
+        if (!h->pool) return fail(VIT_ERR_ARG, "out of host memory");
+    }
+    return VIT_OK;
+}
+
+// Time-sliced upload: ONE decode launch starts at once and every warp waits at "upload gates" for the next column block
+// of its segments; the copy stream uploads block b of EVERY segment (two strided copies: the first P%W segments are one
+// pack longer) and then opens gate b.  The decode therefore finishes one short block after the last byte has landed,
+// instead of a whole per-segment chain (0.25-0.4 ms) after it as with segment-range chunks.
+//   pinned caller buffers: the copies read the caller's input in place;
+//   pageable (stage_in / stage_out): the worker threads first copy block b of every segment into the pinned staging buffer (same
+//                          layout), which overlaps with the upload of block b-1; the decoded packs come back through
+//                          the pinned output staging buffer.
+// *gave_up is set when a warp stopped waiting for a gate (the output is then incomplete).
+int run_gated(vit_handle* h, const HostRun& g, bool stage_in, bool stage_out, bool* gave_up) {
+    const bool staged = stage_in || stage_out;
     GatePlan gp;
-    // column blocks of 1/2, 3/8 and 1/8 of a segment (profiles/r1_upload_pattern_probe.txt): fewer, wider strided copies
-    // upload faster (0.66 ms for 32 MB against 0.69 with four blocks), a short last block keeps the tail short
-    // That is for inputs whose upload takes longer than their decode (>= 1 byte per decoded bit at ~50 GB/s against
-    // 12-16 ps per bit).  Hard-decision input (0.25 byte per bit) is decode bound: a small first block lets the kernel start
-    // early and the rest arrives long before it is needed.
-    gp.n = 3;
-    gp.super[0] = 0;
-    if (in_type(h->options) == 0) { gp.super[1] = (unsigned)(g.nsuper / 8); gp.super[2] = (unsigned)(g.nsuper / 2); }
-    else { gp.super[1] = (unsigned)(g.nsuper / 2); gp.super[2] = (unsigned)(g.nsuper * 7 / 8); }
+    if (stage_in) {
+        // equal column blocks: the staging copy of block b+1 hides behind the upload of block b
+        gp.n = (unsigned)std::min<size_t>(8, std::max<size_t>(2, g.nsuper / 4));
+        for (unsigned b = 0; b < gp.n; b++) gp.super[b] = (unsigned)(g.nsuper * b / gp.n);
+    } else {
+        // column blocks of 1/2, 3/8 and 1/8 of a segment (profiles/r1_upload_pattern_probe.txt): fewer, wider strided
+        // copies upload faster (0.66 ms for 32 MB against 0.69 with four blocks), a short last block keeps the tail
+        // short.  That is for inputs whose upload takes longer than their decode (>= 1 byte per decoded bit at ~50 GB/s
+        // against 12-16 ps per bit).  Hard-decision input (0.25 byte per bit) is decode bound: a small first block lets
+        // the kernel start early and the rest arrives long before it is needed.
+        gp.n = 3;
+        gp.super[0] = 0;
+        if (in_type(h->options) == 0) { gp.super[1] = (unsigned)(g.nsuper / 8); gp.super[2] = (unsigned)(g.nsuper / 2); }
+        else { gp.super[1] = (unsigned)(g.nsuper / 2); gp.super[2] = (unsigned)(g.nsuper * 7 / 8); }
+    }
     VIT_CUDA(cudaStreamSynchronize(h->stream));           // a kernel abandoned by a failed earlier call may still own the error word
     h->epoch_h[16] = 0;
     h->epoch++;
@@ -244,19 +388,24 @@ int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
     static const bool dbg = getenv("VIT_RUN_DEBUG") != nullptr;
     auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
     const double t_begin = dbg ? now() : 0.0;
+    // a warp gives up on a gate after the time the whole upload would take at 1 GB/s plus 0.2 s (a healthy upload runs
+    // at ~50 GB/s): long enough for any working configuration, short enough not to look like a hang
+    h->gate_timeout_ns = 200000000ull + (unsigned long long)g.in_bytes;
     int rc = launch_range(h, h->in_d, h->out_d, g.inputNum, 1, 0, 0, h->stream, 0, (unsigned)g.W, nullptr, h->ev_kdone, &gp);
     if (rc) return rc;
-    // (storing the decoded packs straight into pinned host memory instead was measured: 4-byte stores over PCIe double
-    // the time of the PCIe-bound s4 case)
-    VIT_CUDA(cudaMemcpyAsync(g.out_h, h->out_d, g.out_bytes, cudaMemcpyDeviceToHost, h->stream));
-    const char* src = g.in_h;
+    const char* user = g.in_h;
+    char* stage = static_cast<char*>(h->pin_in);
+    const char* src = stage_in ? stage : user;
     char* dst = static_cast<char*>(h->in_d);
     const size_t pitch1 = (g.q + 1) * g.pack_bytes, pitch2 = g.q * g.pack_bytes;   // segment strides in bytes
     const size_t grp2 = g.r * pitch1;                                                // first byte of segment r
     const size_t body_end = g.P * g.pack_bytes;                                      // first byte after the last segment's own packs
+    if (staged) h->pool->begin_call();
     // the last 64 stages of the stream (warm-up tail of the last segment) go with the first block
-    if (g.in_bytes > body_end)
+    if (g.in_bytes > body_end) {
+        if (stage_in) memcpy(stage + body_end, user + body_end, g.in_bytes - body_end);
         VIT_CUDA(cudaMemcpyAsync(dst + body_end, src + body_end, g.in_bytes - body_end, cudaMemcpyHostToDevice, h->copy_stream));
+    }
     static const bool lose_gate = getenv("VIT_TEST_LOSE_GATE") != nullptr;           // test hook: never open the last gate
     for (unsigned b = 0; b < gp.n; b++) {
         // columns [lo, hi) of every segment row: super-steps [super[b], super[b+1]) plus the read-ahead the kernel's
@@ -264,6 +413,18 @@ int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
         const size_t lo = b == 0 ? 0 : (size_t)gp.super[b] * g.b96 - 16;
         const size_t hi = b + 1 == gp.n ? (size_t)-1 : (size_t)gp.super[b + 1] * g.b96 + 48;
         const size_t w1 = std::min(hi, pitch1), w2 = std::min(hi, pitch2);
+        if (stage_in) {
+            // rows are dealt to the workers in groups of 32 (a group of short rows is still tens of kilobytes)
+            const size_t groups = (g.W + 31) / 32;
+            const std::function<void(size_t)> job = [&](size_t gi) {
+                for (size_t w = gi * 32; w < std::min(g.W, gi * 32 + 32); w++) {
+                    const size_t row = w < g.r ? w * pitch1 : grp2 + (w - g.r) * pitch2;
+                    const size_t wd = w < g.r ? w1 : w2;
+                    if (wd > lo) memcpy(stage + row + lo, user + row + lo, wd - lo);
+                }
+            };
+            h->pool->parallel_for(groups, job);
+        }
         if (g.r && w1 > lo)
             VIT_CUDA(cudaMemcpy2DAsync(dst + lo, pitch1, src + lo, pitch1, w1 - lo, g.r, cudaMemcpyHostToDevice, h->copy_stream));
         if (w2 > lo)
@@ -271,6 +432,12 @@ int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
         if (lose_gate && b + 1 == gp.n) continue;
         VIT_CUDA(cudaMemcpyAsync(h->gate_d + b, h->epoch_h, sizeof(unsigned), cudaMemcpyHostToDevice, h->copy_stream));
     }
+    // The download is queued only now, after every upload: a device-to-host copy into PAGEABLE memory blocks the host
+    // until it has run, i.e. until the kernel is done -- queued earlier it would keep the uploads the kernel waits for
+    // from ever being issued.  (Storing the decoded packs straight into pinned host memory from the kernel was measured:
+    // 4-byte stores over PCIe double the time of the PCIe-bound s4 case.)
+    char* out_target = stage_out ? static_cast<char*>(h->pin_out) : g.out_h;
+    VIT_CUDA(cudaMemcpyAsync(out_target, h->out_d, g.out_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (dbg) {
         const double t_issued = now();
         cudaStreamSynchronize(h->copy_stream);
@@ -278,13 +445,27 @@ int run_gated(vit_handle* h, const HostRun& g, bool* gave_up) {
         cudaEventSynchronize(h->ev_kdone);
         const double t_kernel = now();
         cudaStreamSynchronize(h->stream);
-        fprintf(stderr, "[vit_run gated] issue %.3f ms, upload done +%.3f, kernel done +%.3f, download done +%.3f\n",
-                t_issued - t_begin, t_copy - t_begin, t_kernel - t_begin, now() - t_begin);
+        fprintf(stderr, "[vit_run gated%s] issue %.3f ms, upload done +%.3f, kernel done +%.3f, download done +%.3f\n",
+                staged ? " staged" : "", t_issued - t_begin, t_copy - t_begin, t_kernel - t_begin, now() - t_begin);
     }
-    VIT_CUDA(cudaStreamSynchronize(h->copy_stream));
-    VIT_CUDA(cudaStreamSynchronize(h->stream));
+    cudaError_t e = cudaStreamSynchronize(h->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        if (staged) h->pool->end_call();
+        return fail(VIT_ERR_CUDA, "%s in %s at line %d", cudaGetErrorString(e), __FILE__, __LINE__);
+    }
     *gave_up = *static_cast<volatile unsigned*>(h->epoch_h + 16) != 0;
     h->epoch_h[16] = 0;
+    if (staged) {
+        if (stage_out && !*gave_up) {
+            const size_t piece = 256u << 10, n = (g.out_bytes + piece - 1) / piece;
+            const std::function<void(size_t)> job = [&](size_t i) {
+                memcpy(g.out_h + i * piece, out_target + i * piece, std::min(piece, g.out_bytes - i * piece));
+            };
+            h->pool->parallel_for(n, job);
+        }
+        h->pool->end_call();
+    }
     return VIT_OK;
 }
 
@@ -380,10 +561,15 @@ int vit_create(vit_handle** out, int options, int device, size_t prealloc_inputN
     if (!out) return fail(VIT_ERR_ARG, "null handle pointer");
     *out = nullptr;
     if (!vit_options_valid(options)) return fail(VIT_ERR_OPTIONS, "unsupported option combination 0x%x", options);
-    VIT_CUDA(cudaSetDevice(device));
+    DeviceGuard guard_;
+    VIT_CUDA(guard_.enter(device));
     vit_handle* h = new (std::nothrow) vit_handle();
     if (!h) return fail(VIT_ERR_ARG, "out of host memory");
     h->options = options; h->device = device; h->kernel = entry_for(options);
+    if (const char* e = getenv("VIT_RUN_MODE")) {            // same values as vit_set_upload_mode
+        const int m = atoi(e);
+        if (m >= VIT_UPLOAD_AUTO && m <= VIT_UPLOAD_GATED) h->upload_mode = m;
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
@@ -414,9 +600,11 @@ int vit_create(vit_handle** out, int options, int device, size_t prealloc_inputN
 
 void vit_destroy(vit_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_;
+    guard_.enter(h->device);
     if (h->in_d) cudaFree(h->in_d);
     if (h->out_d) cudaFree(h->out_d);
+    delete h->pool;
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -447,7 +635,7 @@ unsigned long long vit_launch_count(const vit_handle* h) { return h ? h->launche
 int vit_run_device_batch(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t nstreams,
                          size_t in_stride, size_t out_stride, void* cuda_stream, float* kernel_ms) {
     if (!h || !in_d || !out_d) return fail(VIT_ERR_ARG, "null argument");
-    VIT_CUDA(cudaSetDevice(h->device));
+    VIT_ON_DEVICE(h);
     return launch(h, in_d, out_d, inputNum, nstreams, in_stride, out_stride, static_cast<cudaStream_t>(cuda_stream), kernel_ms);
 }
 
@@ -457,31 +645,49 @@ int vit_run_device(vit_handle* h, const void* in_d, void* out_d, size_t inputNum
 
 int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float* kernel_ms) {
     if (!h || !in_h || !out_h) return fail(VIT_ERR_ARG, "null argument");
-    VIT_CUDA(cudaSetDevice(h->device));
+    VIT_ON_DEVICE(h);
     const size_t in_bytes = vit_input_size(h->options, inputNum);
     const size_t out_bytes = vit_output_size(h->options, inputNum);
     if (out_bytes == 0) { if (kernel_ms) *kernel_ms = 0.f; return VIT_OK; }
     int rc = ensure_device_buffers(h, in_bytes, out_bytes);
     if (rc) return rc;
     const HostRun hr = host_run_geometry(h, in_h, out_h, inputNum);
-    // VIT_RUN_MODE=2 (measurement hook) forces the segment-range chunk pipeline where the time-sliced upload would be used
-    static const int run_mode = [] { const char* e = getenv("VIT_RUN_MODE"); return e ? atoi(e) : 0; }();
-    if (kernel_ms || hr.W < 64) return run_sequential(h, hr, kernel_ms);
-    // Pageable host memory is staged by the driver, synchronously and piece by piece: nothing overlaps, and one large
-    // copy is the fastest way through (32 MB s4 stream: 2.3 ms sequential, 3.9 ms through the chunk pipeline).  Callers who
-    // want the overlap allocate their buffers with vit_host_alloc / cudaHostAlloc / cudaHostRegister.
-    if (!is_pinned(in_h)) return run_sequential(h, hr, nullptr);
-    if (run_mode == 0 && gated_upload_applies(h, hr)) {
+    // A kernel-time request keeps the reference's exact copy -> launch -> copy sequence (viterbi.cu:219-235): the time
+    // between the events is then the decode alone, as the reference reports it.
+    if (kernel_ms || hr.W < 64 || h->upload_mode == VIT_UPLOAD_SEQUENTIAL) return run_sequential(h, hr, kernel_ms);
+    const bool pin_in = is_pinned(in_h), pin_out = is_pinned(out_h);
+    if (h->upload_mode != VIT_UPLOAD_CHUNKED && gated_upload_applies(h, hr)) {
+        // pageable buffers (the reference's calling convention: std::vector storage, viterbiDF.h:188-193) go through the
+        // pinned staging buffers, copied by the worker threads block by block
+        if (!pin_in || !pin_out) {
+            rc = ensure_staging(h, pin_in ? 0 : in_bytes, pin_out ? 0 : out_bytes);
+            if (rc) return rc;
+        }
         bool gave_up = false;
-        rc = run_gated(h, hr, &gave_up);
+        rc = run_gated(h, hr, !pin_in, !pin_out, &gave_up);
         if (rc || !gave_up) return rc;
-        // A warp gave up waiting for its upload gate: something (a profiler that serialises kernels and copies, an
-        // exhausted copy queue) kept the copies from running beside the kernel.  Nothing was lost: decode again with
-        // the chunk pipeline and stop using gates on this handle.
+        // A warp gave up waiting for its upload gate: something kept the copies from running beside the kernel.
+        // Nothing was lost: decode again below and stop using gates on this handle.
         h->gates_disabled = true;
+        if (h->upload_mode == VIT_UPLOAD_GATED) return fail(VIT_ERR_CUDA, "upload gate timed out (copies do not overlap kernels in this environment)");
     }
-    if (hr.nch < 2) return run_sequential(h, hr, nullptr);
+    // Without gates: pinned buffers take the segment-range chunk pipeline; pageable memory is staged by the driver,
+    // synchronously and piece by piece, so one large copy is the fastest way through.
+    if (!pin_in || !pin_out || hr.nch < 2) return run_sequential(h, hr, nullptr);
     return run_chunked(h, hr);
+}
+
+int vit_set_upload_mode(vit_handle* h, int mode) {
+    if (!h) return fail(VIT_ERR_ARG, "null handle");
+    if (mode < VIT_UPLOAD_AUTO || mode > VIT_UPLOAD_GATED) return fail(VIT_ERR_ARG, "unknown upload mode %d", mode);
+    h->upload_mode = mode;
+    return VIT_OK;
+}
+
+int vit_upload_mode_in_effect(const vit_handle* h) {
+    if (!h) return -1;
+    if (h->upload_mode != VIT_UPLOAD_AUTO) return h->upload_mode;
+    return h->gates_disabled ? VIT_UPLOAD_CHUNKED : VIT_UPLOAD_GATED;
 }
 
 #pragma GCC visibility pop

@@ -75,6 +75,7 @@ struct KParams {
     unsigned gate_epoch;
     unsigned gate_n;
     unsigned gate_super[8];
+    unsigned long long gate_timeout_ns;   // a warp gives up on a gate after this long (vit_api.cu derives it from the copy size)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -114,20 +115,23 @@ VIT_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memo
 template <int N> VIT_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 VIT_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 VIT_D uint32_t brev32(uint32_t v) { return __brev(v); }
-// wait until *flag == epoch (written by the host's copy stream after the slice's bytes); gives up after ~2 s
-VIT_D bool gate_spin(const unsigned* flag, unsigned epoch) {
+// wait until *flag == epoch (written by the host's copy stream after the slice's bytes); gives up after timeout_ns.
+// The verdict is warp-uniform (every lane polls, the warp votes): no lane may leave while others go on to shuffles.
+VIT_D bool gate_spin(const unsigned* flag, unsigned epoch, unsigned long long timeout_ns) {
     unsigned long long t0 = 0;
     for (unsigned it = 1;; it++) {
         unsigned v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (v == epoch) return true;
+        if (__all_sync(0xffffffffu, v == epoch)) return true;
         __nanosleep(it < 8 ? 200 : 1000);
-        if ((it & 255u) == 0) {
+        bool expired = false;
+        if ((it & 63u) == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 2000000000ull) return false;
+            else expired = now - t0 > timeout_ns;
         }
+        if (__any_sync(0xffffffffu, expired)) return false;
     }
 }
 #else
@@ -160,7 +164,7 @@ inline uint32_t brev32(uint32_t v) {
     for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
     return r;
 }
-inline bool gate_spin(const unsigned* flag, unsigned epoch) { return *flag == epoch; }
+inline bool gate_spin(const unsigned* flag, unsigned epoch, unsigned long long) { return *flag == epoch; }
 #endif
 
 // ------------------------------------------------------------------------------------------------

@@ -5,7 +5,9 @@
 //
 // Everything is counter based and integer only, so the CPU twin (oracle.make_channel_det(bits_source="hash"),
 // test infrastructure) reproduces it bit for bit:
-//   message bit i       = top bit of splitmix64(i + seed * 0xD1B54A32D192ED03)
+//   message bit i       = top bit of splitmix64(i + seed * 0xD1B54A32D192ED03)   (source 0), or
+//                         bit i of the PRBS-31 sequence x^31 + x^28 + 1 started from state `seed` (source 1: the
+//                         bench's message source; CPU twin vo_prbs31)
 //   coded symbols 2i,2i+1 = parities of the 7-bit buffer (bit 6 = newest) with 0171 / 0133   (viterbiDF.h:48-60)
 //   symbol value (Q8)   = +-(amp << 8) + ((u * sigma_q16) >> 16),  u = sum of the four 16-bit lanes of
 //                         splitmix64(j + seed * 0x100000001B3) - 2*65535   (~Gaussian, sd = 0.577 * sigma_q16 / 256)
@@ -30,12 +32,72 @@ struct SynthParams {
     unsigned long long n_bits, seed;
     long long amp_q8, sigma_q16;
     int input_type, zero;
+    int source;                  // 0: counter hash, 1: PRBS-31
 };
 
-__device__ inline int msg_bit(const SynthParams& p, long long i) {
-    if (i < 0) return 0;                                   // encoder starts from the all-zero state
-    return (int)(splitmix64((uint64_t)i + p.seed * 0xD1B54A32D192ED03ull) >> 63);
+// ---- PRBS-31 (x^31 + x^28 + 1), the bench's message source (oracle twin: vo_prbs31) ----------------
+// state s (31 bits), one step: nb = s[30] ^ s[27]; s = (s << 1) | nb; output nb.  Bit i of the sequence is the output
+// of step i from s_0 = seed.  To start anywhere, the state is advanced by i steps with the precomputed powers
+// T^(2^j) of the step matrix (columns = images of the unit vectors).
+constexpr int PRBS_POWERS = 40;
+__constant__ uint32_t c_prbs_pow[PRBS_POWERS][31];
+
+inline uint32_t prbs_step_host(uint32_t s) {
+    const uint32_t nb = ((s >> 30) ^ (s >> 27)) & 1u;
+    return ((s << 1) | nb) & 0x7fffffffu;
 }
+inline uint32_t matvec_host(const uint32_t* col, uint32_t v) {
+    uint32_t r = 0;
+    for (int k = 0; k < 31; k++) if ((v >> k) & 1u) r ^= col[k];
+    return r;
+}
+cudaError_t upload_prbs_tables() {
+    static uint32_t tab[PRBS_POWERS][31];
+    static bool done[64] = {};                                       // per device (constant memory is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    for (int k = 0; k < 31; k++) tab[0][k] = prbs_step_host(1u << k);
+    for (int j = 1; j < PRBS_POWERS; j++)
+        for (int k = 0; k < 31; k++) tab[j][k] = matvec_host(tab[j - 1], tab[j - 1][k]);
+    const cudaError_t e = cudaMemcpyToSymbol(c_prbs_pow, tab, sizeof tab);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+__device__ inline uint32_t prbs_jump(uint32_t s, unsigned long long steps) {
+    for (int j = 0; steps; j++, steps >>= 1) {
+        if (!(steps & 1ull)) continue;
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 31; k++) r ^= ((s >> k) & 1u) ? c_prbs_pow[j][k] : 0u;
+        s = r;
+    }
+    return s;
+}
+__host__ __device__ inline uint32_t prbs_seed_state(unsigned long long seed) {
+    uint32_t s = (uint32_t)seed & 0x7fffffffu;
+    return s ? s : 0x7fffffffu;
+}
+
+// sequential reader of the message bits from index `i` on (i may be negative: the encoder starts from zeros)
+struct BitReader {
+    const SynthParams& p;
+    long long i;
+    uint32_t s;
+    __device__ BitReader(const SynthParams& p_, long long i0) : p(p_), i(i0), s(0) {
+        if (p.source == 1) s = prbs_jump(prbs_seed_state(p.seed), i0 > 0 ? (unsigned long long)i0 : 0ull);
+    }
+    __device__ int next() {
+        int b;
+        if (i < 0) b = 0;
+        else if (p.source == 1) {
+            b = (int)(((s >> 30) ^ (s >> 27)) & 1u);
+            s = ((s << 1) | (uint32_t)b) & 0x7fffffffu;
+        } else b = (int)(splitmix64((uint64_t)i + p.seed * 0xD1B54A32D192ED03ull) >> 63);
+        i++;
+        return b;
+    }
+};
 
 __device__ inline long long symbol_value(const SynthParams& p, unsigned long long j, int coded) {
     if (p.zero) return 0;
@@ -48,38 +110,42 @@ __device__ inline long long symbol_value(const SynthParams& p, unsigned long lon
     return v >> 8;
 }
 
-// one thread = one 32-bit pack (HARD 16 message bits, SOFT4 4, SOFT8 2, SOFT16 1) or one symbol pair (FP32)
+// one thread = WPT consecutive 32-bit packs (HARD 16 message bits each, SOFT4 4, SOFT8 2, SOFT16 1) or symbol pairs (FP32)
+constexpr int WPT = 8;
 __global__ void synth_kernel(SynthParams p, uint32_t* __restrict__ packed, uint8_t* __restrict__ bits_out,
                              unsigned long long n_words) {
-    const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
+    const unsigned long long w0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * WPT;
+    if (w0 >= n_words) return;
     const int bits_per_word = p.input_type == 0 ? 16 : p.input_type == 1 ? 4 : p.input_type == 2 ? 2 : 1;
-    const long long i0 = (long long)w * bits_per_word;
+    const long long i0 = (long long)w0 * bits_per_word;
+    BitReader rd(p, i0 - 6);
     unsigned sr = 0;                                        // encoder buffer, bit 6 = newest
-    for (int k = 6; k >= 1; k--) sr = (sr >> 1) | ((unsigned)msg_bit(p, i0 - k) << 6);
-    uint32_t word = 0;
-    float f[2] = {0.f, 0.f};
-    for (int b = 0; b < bits_per_word; b++) {
-        const long long i = i0 + b;
-        const int u = (unsigned long long)i < p.n_bits ? msg_bit(p, i) : 0;
-        if (bits_out && (unsigned long long)i < p.n_bits) bits_out[i] = (uint8_t)u;
-        sr = (sr >> 1) | ((unsigned)u << 6);
-        const int c[2] = {__popc(sr & 0171) & 1, __popc(sr & 0133) & 1};
-        for (int k = 0; k < 2; k++) {
-            long long v = (unsigned long long)i < p.n_bits ? symbol_value(p, 2ull * i + k, c[k]) : 0;
-            switch (p.input_type) {
-                case 0: word = (word << 1) | (v > 0 ? 1u : 0u); break;
-                case 1: v = v < -8 ? -8 : v > 7 ? 7 : v; word = (word << 4) | ((uint32_t)v & 0xFu); break;
-                case 2: v = v < -128 ? -128 : v > 127 ? 127 : v; word = (word << 8) | ((uint32_t)v & 0xFFu); break;
-                case 3: v = v < -32768 ? -32768 : v > 32767 ? 32767 : v; word = (word << 16) | ((uint32_t)v & 0xFFFFu); break;
-                default: f[k] = (float)v / 16.0f; break;
+    for (int k = 0; k < 6; k++) sr = (sr >> 1) | ((unsigned)rd.next() << 6);
+    for (int ww = 0; ww < WPT && w0 + ww < n_words; ww++) {
+        const unsigned long long w = w0 + ww;
+        uint32_t word = 0;
+        float f[2] = {0.f, 0.f};
+        for (int b = 0; b < bits_per_word; b++) {
+            const long long i = (long long)w * bits_per_word + b;
+            const bool live = (unsigned long long)i < p.n_bits;
+            int u = rd.next();
+            if (!live) u = 0;
+            if (bits_out && live) bits_out[i] = (uint8_t)u;
+            sr = (sr >> 1) | ((unsigned)u << 6);
+            const int c[2] = {__popc(sr & 0171) & 1, __popc(sr & 0133) & 1};
+            for (int k = 0; k < 2; k++) {
+                long long v = live ? symbol_value(p, 2ull * i + k, c[k]) : 0;
+                switch (p.input_type) {
+                    case 0: word = (word << 1) | (v > 0 ? 1u : 0u); break;
+                    case 1: v = v < -8 ? -8 : v > 7 ? 7 : v; word = (word << 4) | ((uint32_t)v & 0xFu); break;
+                    case 2: v = v < -128 ? -128 : v > 127 ? 127 : v; word = (word << 8) | ((uint32_t)v & 0xFFu); break;
+                    case 3: v = v < -32768 ? -32768 : v > 32767 ? 32767 : v; word = (word << 16) | ((uint32_t)v & 0xFFFFu); break;
+                    default: f[k] = (float)v / 16.0f; break;
+                }
             }
         }
-    }
-    if (p.input_type == 4) {
-        reinterpret_cast<float2*>(packed)[w] = make_float2(f[0], f[1]);
-    } else {
-        packed[w] = word;
+        if (p.input_type == 4) reinterpret_cast<float2*>(packed)[w] = make_float2(f[0], f[1]);
+        else packed[w] = word;
     }
 }
 
@@ -101,6 +167,23 @@ __global__ void count_errors_kernel(const void* __restrict__ out, const uint8_t*
     if ((threadIdx.x & 31) == 0 && errs) atomicAdd(total, errs);
 }
 
+// the same count with the message bits regenerated from the source (no bits buffer): one thread = one pack
+template <int BPP>
+__global__ void count_errors_synth_kernel(SynthParams p, const void* __restrict__ out, unsigned long long n_packs,
+                                          unsigned long long* __restrict__ total) {
+    unsigned long long errs = 0;
+    const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n_packs) {
+        const uint32_t word = BPP == 16 ? static_cast<const uint16_t*>(out)[w] : static_cast<const uint32_t*>(out)[w];
+        BitReader rd(p, (long long)(w * BPP + 26));
+        uint32_t gen = 0;
+        for (int k = 0; k < BPP; k++) gen = (gen << 1) | (uint32_t)rd.next();
+        errs = __popc(word ^ gen);
+    }
+    for (int d = 16; d > 0; d >>= 1) errs += __shfl_down_sync(0xffffffffu, errs, d);
+    if ((threadIdx.x & 31) == 0 && errs) atomicAdd(total, errs);
+}
+
 }  // namespace
 
 extern "C" {
@@ -109,24 +192,56 @@ extern "C" {
 // Fill packed_d (vit_input_size(options, 2*n_bits) bytes, rounded up to whole 32-bit packs) with a synthetic
 // received stream for n_bits message bits; bits_d (optional, n_bits bytes) receives the message bits for BER.
 // amp: symbol amplitude in quantiser units (0 = default per input type); sigma: noise sd relative to amp.
-int vit_synth_device(int input_type, size_t n_bits, unsigned seed, int amp, double sigma, int zero,
-                     void* packed_d, void* bits_d, void* cuda_stream) {
-    if (input_type < 0 || input_type > 4 || !packed_d) return VIT_ERR_ARG;
+int vit_synth_device_ex(int input_type, size_t n_bits, unsigned seed, int amp, double sigma, int zero, int source,
+                        void* packed_d, void* bits_d, void* cuda_stream) {
+    if (input_type < 0 || input_type > 4 || !packed_d || source < 0 || source > 1) return VIT_ERR_ARG;
     static const int def_amp[5] = {64, 3, 40, 9000, 48};
     if (amp <= 0) amp = def_amp[input_type];
     SynthParams p;
-    p.n_bits = n_bits; p.seed = seed; p.input_type = input_type; p.zero = zero;
+    p.n_bits = n_bits; p.seed = seed; p.input_type = input_type; p.zero = zero; p.source = source;
+    if (source == 1 && upload_prbs_tables() != cudaSuccess) return VIT_ERR_CUDA;
     p.amp_q8 = (long long)amp << 8;
     p.sigma_q16 = (long long)(sigma * amp * 256.0 / 0.57735 + 0.5);
     const int bits_per_word = input_type == 0 ? 16 : input_type == 1 ? 4 : input_type == 2 ? 2 : 1;
     const unsigned long long n_words = (n_bits + bits_per_word - 1) / bits_per_word;
     if (n_words == 0) return VIT_OK;
     const unsigned threads = 256;
-    const unsigned long long blocks = (n_words + threads - 1) / threads;
+    const unsigned long long blocks = ((n_words + WPT - 1) / WPT + threads - 1) / threads;
     if (blocks > 0x7fffffffull) return VIT_ERR_ARG;
     synth_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
         p, static_cast<uint32_t*>(packed_d), static_cast<uint8_t*>(bits_d), n_words);
     return cudaGetLastError() == cudaSuccess ? VIT_OK : VIT_ERR_CUDA;
+}
+
+int vit_synth_device(int input_type, size_t n_bits, unsigned seed, int amp, double sigma, int zero,
+                     void* packed_d, void* bits_d, void* cuda_stream) {
+    return vit_synth_device_ex(input_type, n_bits, seed, amp, sigma, zero, 0, packed_d, bits_d, cuda_stream);
+}
+
+// Bit errors against the message bits of the synthetic source itself (regenerated on the fly: no bits buffer, which
+// for multi-Gbit streams would be larger than the decoded output by 8x).  Synchronous.
+int vit_count_errors_synth_device(int options, const void* out_d, size_t messageLen, unsigned seed, int source,
+                                  unsigned long long* errors, void* cuda_stream) {
+    if (!out_d || !errors || source < 0 || source > 1) return VIT_ERR_ARG;
+    const int bpp = ((options >> 8) & 0xf) == 1 ? 16 : 32;
+    SynthParams p{};
+    p.seed = seed; p.source = source; p.n_bits = ~0ull;
+    if (source == 1 && upload_prbs_tables() != cudaSuccess) return VIT_ERR_CUDA;
+    unsigned long long* acc = nullptr;
+    if (cudaMalloc(&acc, sizeof *acc) != cudaSuccess) return VIT_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaMemsetAsync(acc, 0, sizeof *acc, st);
+    const unsigned long long n_packs = messageLen / bpp;
+    if (n_packs) {
+        const unsigned long long blocks = (n_packs + 255) / 256;
+        if (blocks > 0x7fffffffull) { cudaFree(acc); return VIT_ERR_ARG; }
+        if (bpp == 16) count_errors_synth_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(p, out_d, n_packs, acc);
+        else count_errors_synth_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(p, out_d, n_packs, acc);
+    }
+    cudaError_t e = cudaMemcpyAsync(errors, acc, sizeof *acc, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(acc);
+    return e == cudaSuccess ? VIT_OK : VIT_ERR_CUDA;
 }
 
 // Bit errors of a decoded stream against the message bits (one byte per bit, e.g. from vit_synth_device),

@@ -52,6 +52,25 @@ void vit_destroy(vit_handle* h);
  * measured with CUDA events around the launch only, as the reference does (viterbi.cu:224-232). */
 int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float* kernel_ms);
 
+/* How vit_run moves host buffers (default VIT_UPLOAD_AUTO; the environment variable VIT_RUN_MODE=<value> sets the
+ * initial mode of every handle).  Results are identical in every mode.
+ *   AUTO        time-sliced upload (one decode launch that waits, inside the kernel, for column blocks of its input)
+ *               when copies can run beside kernels, otherwise as CHUNKED.  Pinned buffers are read/written in place;
+ *               pageable buffers (the reference's calling convention, viterbiDF.h:188-193) are staged through pinned
+ *               buffers by worker threads (VIT_STAGE_THREADS, default min(8, cores/2)).  A run with kernel_ms != NULL
+ *               always takes the SEQUENTIAL path, so that the reported time is the decode kernel alone.
+ *   SEQUENTIAL  the reference's copy -> launch -> copy sequence (viterbi.cu:219-235).
+ *   CHUNKED     segment-range pipeline: pinned buffers only, pageable buffers fall back to SEQUENTIAL.
+ *   GATED       insist on the time-sliced upload (fails instead of falling back if an upload gate times out).
+ * AUTO avoids the time-sliced upload up front under CUDA_DEVICE_MAX_CONNECTIONS=1, CUDA_LAUNCH_BLOCKING=1 and under
+ * tools injected into the CUDA driver (ncu, nsys, compute-sanitizer), where a copy issued after a kernel cannot run
+ * before that kernel ends; should a gate still time out (copy size / 1 GB/s + 0.2 s), the call decodes again through
+ * the fallback and the handle stops using gates. */
+enum { VIT_UPLOAD_AUTO = 0, VIT_UPLOAD_SEQUENTIAL = 1, VIT_UPLOAD_CHUNKED = 2, VIT_UPLOAD_GATED = 3 };
+int vit_set_upload_mode(vit_handle* h, int mode);
+/* the mode AUTO currently resolves to (GATED or CHUNKED), or the mode that was set */
+int vit_upload_mode_in_effect(const vit_handle* h);
+
 /* device-resident variant (no copies): in_d must be 16-byte aligned and hold vit_input_size()
  * bytes; out_d receives vit_output_size() bytes.  cuda_stream is a cudaStream_t (NULL = default
  * stream).  Asynchronous unless kernel_ms is non-NULL.  New relative to the reference: needed for
@@ -96,6 +115,16 @@ int vit_set_segments(vit_handle* h, unsigned segments);
 int vit_synth_device(int input_type, size_t n_bits, unsigned seed, int amp, double sigma, int zero,
                      void* packed_d, void* bits_d, void* cuda_stream);
 
+/* the same with a choice of message source: 0 = counter hash (vit_synth_device), 1 = PRBS-31 (x^31 + x^28 + 1 started
+ * from state `seed`; the bench's source) */
+int vit_synth_device_ex(int input_type, size_t n_bits, unsigned seed, int amp, double sigma, int zero, int source,
+                        void* packed_d, void* bits_d, void* cuda_stream);
+
+/* Bit errors of a decoded stream against the message bits of the synthetic source itself, regenerated on the fly (no
+ * bits buffer: for multi-Gbit streams it would be 8x the decoded output).  Synchronous. */
+int vit_count_errors_synth_device(int options, const void* out_d, size_t messageLen, unsigned seed, int source,
+                                  unsigned long long* errors, void* cuda_stream);
+
 /* Bit errors of a decoded stream counted on the device: #{ j < messageLen : out bit j != bits[j + 26] }
  * (the reference's BER loop, src/main.cpp:153-169); bits_d holds one byte per message bit.  Synchronous. */
 int vit_count_errors_device(int options, const void* out_d, const void* bits_d, size_t messageLen,
@@ -106,8 +135,8 @@ int vit_dev_alloc(void** ptr, size_t bytes);
 void vit_dev_free(void* ptr);
 int vit_dev_sync(void);
 int vit_dev_count(void);
-/* page-locked (pinned) host memory: from such buffers vit_run overlaps upload, decode and download (one launch that waits for
- * time slices of its input); pageable buffers take a slower segment-range chunk pipeline */
+/* page-locked (pinned) host memory: vit_run reads and writes such buffers in place (no staging copy); pageable buffers are
+ * staged through the handle's own pinned buffers by worker threads (see vit_set_upload_mode) */
 int vit_host_alloc(void** ptr, size_t bytes);
 void vit_host_free(void* ptr);
 

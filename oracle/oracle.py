@@ -45,6 +45,10 @@ def lib():
         L.vo_decode.argtypes = [C.c_int, C.c_void_p, C.c_void_p, sz, C.c_int, C.c_int]
         L.vo_decode_segments.restype = C.c_int
         L.vo_decode_segments.argtypes = [C.c_int, C.c_void_p, C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
+        L.vo_segment_window.restype = None
+        L.vo_segment_window.argtypes = [C.c_int, sz, sz, sz] + [C.POINTER(sz)] * 4
+        L.vo_decode_window.restype = C.c_int
+        L.vo_decode_window.argtypes = [C.c_int, C.c_void_p, sz, sz, C.c_void_p, sz, sz, sz, sz, C.c_int]
         L.vo_overrun_words.restype = sz
         L.vo_overrun_words.argtypes = [C.c_int, sz, C.c_void_p, sz]
         L.vo_encode.restype, L.vo_encode.argtypes = None, [C.c_void_p, sz, C.c_void_p]
@@ -90,6 +94,27 @@ def decode(options, packed, input_num, nthreads=0, flags=0, segs=None):
     if rc != 0:
         raise ValueError("oracle does not define option combination 0x%x" % options)
     return out
+
+
+def segment_window(options, input_num, seg_begin, seg_end):
+    """(in_byte0, in_bytes, out_word0, out_words) of segments [seg_begin, seg_end): the input bytes they read and the
+    decoded packs they own."""
+    v = [C.c_size_t(0) for _ in range(4)]
+    lib().vo_segment_window(options, input_num, seg_begin, seg_end, *[C.byref(x) for x in v])
+    return tuple(int(x.value) for x in v)
+
+
+def decode_window(options, in_window, input_num, seg_begin, seg_end, nthreads=0):
+    """Decode segments [seg_begin, seg_end) of a stream of which only the byte range segment_window() reports is given
+    (in_window).  Returns (out_word0, packs) -- for streams too long to hold on the host."""
+    b0, nb, w0, nw = segment_window(options, input_num, seg_begin, seg_end)
+    in_window = np.ascontiguousarray(in_window)
+    assert in_window.nbytes >= nb, (in_window.nbytes, nb)
+    out = np.zeros(nw, out_dtype(options))
+    rc = lib().vo_decode_window(options, _ptr(in_window), b0, nb, _ptr(out), w0, input_num, seg_begin, seg_end, nthreads)
+    if rc != 0:
+        raise ValueError("oracle does not define option combination 0x%x" % options)
+    return w0, out
 
 
 def overrun_words(options, input_num):

@@ -159,6 +159,9 @@ typedef struct {
     size_t M, P;          /* decoded bits, decoded packs */
     uint32_t* overrun;    /* [W][2] values, REF_OVERRUN only */
     uint8_t* overrun_valid;
+    /* window mode (vo_decode_window): `in` holds stream bytes [in_off, in_off + in_avail) only and `out`
+     * points at decoded pack number out_off; whole-stream calls have in_off = out_off = 0, in_avail = in_bytes */
+    size_t in_off, in_avail, out_off;
 } dec_ctx;
 
 static size_t g_segments = VO_SEGMENTS;   /* test hook: vo_set_segments */
@@ -172,6 +175,7 @@ static inline void seg_range(size_t P, int bpp, size_t w, size_t* s0, size_t* L)
 }
 
 static void store_word(const dec_ctx* c, size_t widx, uint32_t v) {
+    widx -= c->out_off;
     if (bits_per_pack(c->options) == 16) ((uint16_t*)c->out)[widx] = (uint16_t)v;
     else ((uint32_t*)c->out)[widx] = v;
 }
@@ -195,9 +199,10 @@ static void decode_segment(const dec_ctx* c, size_t w) {
     size_t byte0 = s0 * num / den;                                   /* s0 is a multiple of 16 */
     size_t need = (T + T_tail + 16) * num / den + 16;
     uint8_t* buf = (uint8_t*)calloc(need, 1);
-    if (byte0 < c->in_bytes) {
-        size_t avail = c->in_bytes - byte0;
-        memcpy(buf, c->in + byte0, avail < need ? avail : need);
+    if (byte0 < c->in_bytes && byte0 >= c->in_off && byte0 < c->in_off + c->in_avail) {
+        size_t avail = c->in_bytes - byte0;                            /* bytes past the stream read as zeros */
+        if (avail > c->in_off + c->in_avail - byte0) avail = c->in_off + c->in_avail - byte0;
+        memcpy(buf, c->in + (byte0 - c->in_off), avail < need ? avail : need);
     }
 
     int sym0[32];
@@ -271,8 +276,8 @@ static void decode_segment(const dec_ctx* c, size_t w) {
     free(buf);
 }
 
-int vo_decode_segments(int options, const void* in, void* out, size_t inputNum,
-                       size_t seg_begin, size_t seg_end, int nthreads, int flags) {
+static int decode_range(int options, const void* in, size_t in_off, size_t in_avail, void* out, size_t out_off,
+                        size_t inputNum, size_t seg_begin, size_t seg_end, int nthreads, int flags) {
     int it = in_type(options), mt = metric_type(options);
     if (it > VO_FP32) return -1;
     if (mt != VO_M_B32 && mt != VO_M_B16 && mt != VO_M_FP16) return -1;
@@ -284,6 +289,7 @@ int vo_decode_segments(int options, const void* in, void* out, size_t inputNum,
     c.M = vo_message_len(options, inputNum);
     c.P = c.M / (size_t)bits_per_pack(options);
     c.overrun = NULL; c.overrun_valid = NULL;
+    c.in_off = in_off; c.in_avail = in_avail < c.in_bytes ? in_avail : c.in_bytes; c.out_off = out_off;
     if (seg_end > g_segments) seg_end = g_segments;
     if (flags & VO_FLAG_REF_OVERRUN) {
         c.overrun = (uint32_t*)calloc(2 * g_segments, sizeof(uint32_t));
@@ -307,6 +313,36 @@ int vo_decode_segments(int options, const void* in, void* out, size_t inputNum,
         free(c.overrun); free(c.overrun_valid);
     }
     return 0;
+}
+
+int vo_decode_segments(int options, const void* in, void* out, size_t inputNum,
+                       size_t seg_begin, size_t seg_end, int nthreads, int flags) {
+    return decode_range(options, in, 0, (size_t)-1, out, 0, inputNum, seg_begin, seg_end, nthreads, flags);
+}
+
+/* the byte range of the input that segments [seg_begin, seg_end) read, and the range of decoded packs they own */
+void vo_segment_window(int options, size_t inputNum, size_t seg_begin, size_t seg_end,
+                       size_t* in_byte0, size_t* in_bytes, size_t* out_word0, size_t* out_words) {
+    const int bpp = bits_per_pack(options);
+    const size_t P = vo_message_len(options, inputNum) / (size_t)bpp, total = vo_input_size(options, inputNum);
+    size_t num, den, s0a, La, s0b, Lb;
+    bytes_per_stage(in_type(options), &num, &den);
+    if (seg_end > g_segments) seg_end = g_segments;
+    seg_range(P, bpp, seg_begin, &s0a, &La);
+    seg_range(P, bpp, seg_end - 1, &s0b, &Lb);
+    size_t b0 = s0a * num / den;
+    size_t b1 = (s0b + EXTRA_L + EXTRA_R + (Lb + SLIDE - 1) / SLIDE * SLIDE + SLIDE + 16) * num / den + 16;
+    if (b1 > total) b1 = total;
+    if (b0 > b1) b0 = b1;
+    *in_byte0 = b0; *in_bytes = b1 - b0;
+    *out_word0 = s0a / (size_t)bpp; *out_words = (s0b + Lb - s0a) / (size_t)bpp;
+}
+
+/* Decode segments [seg_begin, seg_end) of a stream too long to hold on the host: in_window holds the stream's bytes
+ * [in_byte0, in_byte0 + in_bytes) (as vo_segment_window reports them) and out_window receives the packs from out_word0 on. */
+int vo_decode_window(int options, const void* in_window, size_t in_byte0, size_t in_bytes, void* out_window,
+                     size_t out_word0, size_t inputNum, size_t seg_begin, size_t seg_end, int nthreads) {
+    return decode_range(options, in_window, in_byte0, in_bytes, out_window, out_word0, inputNum, seg_begin, seg_end, nthreads, 0);
 }
 
 int vo_decode(int options, const void* in, void* out, size_t inputNum, int nthreads, int flags) {

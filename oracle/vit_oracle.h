@@ -64,6 +64,15 @@ int vo_decode(int options, const void* in, void* out, size_t inputNum, int nthre
 int vo_decode_segments(int options, const void* in, void* out, size_t inputNum,
                        size_t seg_begin, size_t seg_end, int nthreads, int flags);
 
+/* Windowed form for streams too long to hold on the host (BASELINE config 3, 4 Gbit of fp32 input = 32 GB):
+ * vo_segment_window reports the input byte range segments [seg_begin, seg_end) read and the decoded packs they
+ * own; vo_decode_window decodes them from a buffer holding just that byte range into a buffer holding just those
+ * packs.  Same arithmetic as vo_decode_segments. */
+void vo_segment_window(int options, size_t inputNum, size_t seg_begin, size_t seg_end,
+                       size_t* in_byte0, size_t* in_bytes, size_t* out_word0, size_t* out_words);
+int vo_decode_window(int options, const void* in_window, size_t in_byte0, size_t in_bytes, void* out_window,
+                     size_t out_word0, size_t inputNum, size_t seg_begin, size_t seg_end, int nthreads);
+
 /* word indices (in decPack_t units) whose value the reference leaves to a store race
  * (O_B16 over-run); writes up to cap indices, returns the count. */
 size_t vo_overrun_words(int options, size_t inputNum, uint64_t* idx, size_t cap);
