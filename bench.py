@@ -47,11 +47,16 @@ WORKLOADS = {
     "s16_f16_o16_256M": (0x123, 256_000_000, 3.0),  # configs[2]
     "f_b32_o32_4G": (0x004, 4_000_000_000, 15.0),   # configs[3]
     "s8_b16_o32_256M": (0x012, 256_000_000, 15.0),  # configs[4] per-stream shape
+    "config5": (0x012, 256_000_000, 15.0),          # configs[4]: the 1024-stream job over 1/2/4/8 GPUs (--streams to scale it down)
 }
 BYTES_PER_BIT_IN = {0: 0.25, 1: 1.0, 2: 2.0, 3: 4.0, 4: 8.0}
-# DRAM traffic per launch from the committed ncu --set full captures (profiles/): the channel words are read exactly
-# once (32.0 MB); the 4 MB of decoded packs are still in L2 when the kernel ends (dram__bytes_write = 0).
-NCU_DRAM_BYTES = {("s4_b16_o32_32M", 1): 32.0e6}
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of the decode
+# kernel on that workload), with the committed capture it was read from; workloads without a capture report null.
+# The channel words are read exactly once; the decoded packs are still in L2 when the kernel ends (bytes written = 0).
+NCU_DRAM_BYTES = {
+    ("s4_b16_o32_32M", 1): (32.03e6, "profiles/r1_v7_ncu_core_0x011.txt"),
+}
+DEFAULT_STEP_GATHER = "copy"
 N_SM = 148
 
 
@@ -67,72 +72,24 @@ def load_pkg():
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic channel on the device (torch = plumbing; not part of the measured path)
+# synthetic channel: generated on the device by the library's own source (vit_synth_device_ex, csrc/vit_synth.cu)
 # ------------------------------------------------------------------------------------------------
-def make_stream_device(torch, n_bits, input_type, snr_db, seed, device):
-    """Returns (bits int8[n] on device, packed uint8 tensor on device, inputNum)."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    bits = torch.randint(0, 2, (n_bits,), dtype=torch.int8, device=device, generator=g)
-    b = torch.cat([torch.zeros(6, dtype=torch.int8, device=device), bits])
-
-    def par(taps):  # encoder buffer bit t (6 = newest) at step i is bits[i-6+t]; viterbiDF.h:48-60
-        acc = torch.zeros(n_bits, dtype=torch.int8, device=device)
-        for t in taps:
-            acc ^= b[t:t + n_bits]
-        return acc
-    o0, o1 = par([0, 3, 4, 5, 6]), par([0, 1, 3, 4, 6])       # 0171, 0133
-    del b
-    sym = torch.stack([o0, o1], 1).reshape(-1).to(torch.float32) * 2 - 1
-    del o0, o1
-    sigma = 10.0 ** (-snr_db / 5.0)                             # main.cpp:135
-    chunk = 1 << 26
-    for s in range(0, sym.numel(), chunk):
-        sym[s:s + chunk] += torch.randn(min(chunk, sym.numel() - s), device=device, generator=g) * sigma
-    nsym = sym.numel()
-    if input_type == 4:
-        packed = (sym * 40000.0).contiguous().view(torch.uint8)
-    elif input_type == 0:
-        hard = (sym > 0).to(torch.uint8)
-        pad = (-nsym) % 32
-        if pad:
-            hard = torch.cat([hard, torch.zeros(pad, dtype=torch.uint8, device=device)])
-        w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=device)
-        by = (hard.view(-1, 8) * w).sum(1, dtype=torch.int32).to(torch.uint8)      # MSB-first bytes
-        packed = by.view(-1, 4).flip(1).contiguous().view(-1)                      # big-endian word -> LE memory
-    else:
-        width = {1: 4, 2: 8, 3: 16}[input_type]
-        lo, hi = -(1 << (width - 1)), (1 << (width - 1)) - 1
-        q = torch.clamp(torch.round(sym * 40000.0), lo, hi)                        # viterbiDF.h:107-124
-        per = 32 // width
-        pad = (-nsym) % per
-        if pad:
-            q = torch.cat([q, torch.zeros(pad, device=device)])
-        if width == 4:
-            qi = q.to(torch.int16) & 0xF
-            by = ((qi[0::2] << 4) | qi[1::2]).to(torch.uint8)
-            packed = by.view(-1, 4).flip(1).contiguous().view(-1)
-        elif width == 8:
-            packed = q.to(torch.int8).view(torch.uint8).view(-1, 4).flip(1).contiguous().view(-1)
-        else:
-            packed = q.to(torch.int16).view(-1, 2).flip(1).contiguous().view(torch.uint8).view(-1)
-    del sym
-    return bits, packed, 2 * n_bits
+HARNESS_SCALE = 40000          # the reference harness's quantiser scale (main.cpp:137)
 
 
-def count_errors_device(torch, out_u8, bits, M, bpp):
-    """out bit j <-> message bit j+26 (main.cpp:153-169), computed on the device in chunks."""
-    errs = 0
-    wbytes = bpp // 8
-    words_total = M // bpp
-    step = 1 << 22
-    sh = torch.arange(bpp - 1, -1, -1, device=out_u8.device, dtype=torch.int64)
-    for w0 in range(0, words_total, step):
-        w1 = min(words_total, w0 + step)
-        raw = out_u8[w0 * wbytes:w1 * wbytes]
-        words = (raw.view(torch.int16).to(torch.int64) & 0xFFFF) if bpp == 16 else (raw.view(torch.int32).to(torch.int64) & 0xFFFFFFFF)
-        db = ((words.unsqueeze(1) >> sh) & 1).reshape(-1).to(torch.int8)
-        errs += int((db != bits[26 + w0 * bpp:26 + w1 * bpp]).sum().item())
-    return errs
+def make_stream_device(V, torch, n_bits, input_type, snr_db, seed, device, pad_to=None):
+    """PRBS-31 message bits (state = seed) -> K=7 0171/0133 encoder -> BPSK +-amp + noise (sd = 10^(-snr/5) * amp) ->
+    the reference's saturating quantiser and MSB-first packing, all on the device.  amp = 40000 quantiser units, the
+    reference harness's scale (main.cpp:135-137): every soft symbol saturates (4-bit soft input is -8 / +7), exactly as
+    `./main` feeds its decoder.  Returns (packed uint8 tensor on the device, inputNum)."""
+    per = {0: 32, 1: 8, 2: 4, 3: 2, 4: 1}[input_type]
+    nsym = 2 * n_bits
+    nbytes = ((nsym + per - 1) // per) * 4 if input_type != 4 else nsym * 4
+    size = max(nbytes + 64, pad_to or 0)
+    packed = torch.zeros(size, dtype=torch.uint8, device=device)
+    V.synth_device(input_type, n_bits, packed.data_ptr(), None, seed=seed, amp=HARNESS_SCALE, sigma=10.0 ** (-snr_db / 5.0),
+                   source=V.SOURCE_PRBS31)
+    return packed, nsym
 
 
 class ClockSampler:
@@ -261,11 +218,21 @@ def measured_peaks():
     return 6650.0, 1965.0, "fallback"
 
 
+def workload_config(name, options, n_bits, snr, gpus=1):
+    """`config`: identical in both arms (the driver compares the two dicts); run-specific detail goes to `run_info`."""
+    return {"workload": name, "message_bits": n_bits, "options": "0x%03x" % options, "snr_db": snr, "segments": 6400,
+            "source": "PRBS-31 message bits, K=7 0171/0133, BPSK + noise sd 10^(-snr/5), x40000 saturating quantiser "
+                      "(the reference harness's scale: soft symbols saturate, e.g. -8/+7 for 4-bit input)",
+            "l2": "every step reads its input from HBM: inputs rotate over distinct device buffers larger than the 126 MB L2 "
+                  "(reference arm: the stream is uploaded from the host again every step)",
+            "parallelism": "single GPU" if gpus <= 1 else "independent streams sharded over %d GPUs, none split; packed output bits gathered to rank 0" % gpus}
+
+
 def cpu_baseline(options, n_bits, snr, budget_s=12.0):
-    """Golden model on the host cores: whole stream if it is small, else a prefix of segments."""
+    """Golden model on the host cores: whole stream if it is small, else a 32-Mbit stream of the same options."""
     from oracle import oracle as O
     n_cpu = min(n_bits, 32_000_000)
-    bits, packed, N = O.make_channel(n_cpu, options & 0xF, snr_db=snr, seed=5)
+    bits, packed, N = O.make_channel(n_cpu, options & 0xF, snr_db=snr, seed=5, prbs=True)
     M = O.message_len(options, N)
     t0 = time.perf_counter()
     reps = 0
@@ -280,14 +247,14 @@ def cpu_baseline(options, n_bits, snr, budget_s=12.0):
 
 
 def run_reference(args, options, n_bits, snr):
-    """--impl reference: the reference's own CUDA decoder through its own run() (host buffers)."""
+    """--impl reference: the reference's own CUDA decoder through its own run() (pageable host buffers)."""
     from oracle import oracle as O
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     base = {"metric": "decoded Gb/s", "unit": "Gb/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "message_bits": n_bits, "options": "0x%03x" % options, "snr_db": snr}}
+            "config": workload_config(args.workload, options, n_bits, snr, args.gpus)}
     have_gpu = O.ref_lib() is not None and O.ref_lib().ref_device_count() > 0
     if not have_gpu or not O.lib().vo_options_valid_ref(options):
         cb = cpu_baseline(options, n_bits, snr, budget_s=20.0)
@@ -296,7 +263,7 @@ def run_reference(args, options, n_bits, snr):
                      "note": "reference CUDA decoder unavailable for this combination: C golden model (port) on host cores"})
         print(json.dumps(base))
         return
-    bits, packed, N = O.make_channel(min(n_bits, 256_000_000), options & 0xF, snr_db=snr, seed=5)
+    bits, packed, N = O.make_channel(min(n_bits, 256_000_000), options & 0xF, snr_db=snr, seed=5, prbs=True)
     M = O.message_len(options, N)
     for _ in range(args.warmup):
         O.ref_decode(options, packed, N)
@@ -307,15 +274,120 @@ def run_reference(args, options, n_bits, snr):
             kms.append(ms)
     wall = time.perf_counter() - t0
     base.update({
-        "value": M / (statistics.mean(kms) * 1e6), "ms_per_step": statistics.mean(kms), "dtype": "int16x2" if options & 0x10 else "int32",
+        "value": M / (statistics.mean(kms) * 1e6), "ms_per_step": statistics.mean(kms),
+        "dtype": {0x00: "int32", 0x10: "int16x2", 0x20: "f16x2"}[options & 0xF0],
         "gpu_launches": args.steps, "clocks": cs.summary(),
         "e2e": {"value": M * args.steps / wall / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": int(O.input_size(options, N)),
-                "d2h_bytes_per_step": int(O.output_size(options, N))},
+                "d2h_bytes_per_step": int(O.output_size(options, N)), "host_memory": "pageable (numpy), the reference's calling convention",
+                "note": "wall clock of ViterbiCUDA::run incl. its per-call cudaMalloc / pageable cudaMemcpy / cudaFree (viterbi.cu:217-237); "
+                        "compare with our e2e.pageable (same buffers), not only with our pinned e2e.value"},
         "cpu_baseline": {"value": M / (statistics.mean(kms) * 1e6), "unit": "Gb/s", "cores": 0, "kind": "reference",
                          "sample": "reference CUDA decoder (oracle/_ref/libvitref.so, -arch=sm_100) on GPU 0; value = its own cudaEvent kernel time, "
                                    "e2e = wall clock of ViterbiCUDA::run incl. its cudaMalloc/cudaMemcpy/cudaFree"},
     })
     print(json.dumps(base))
+
+
+def make_comm(V, torch, dist, world, rank, local, dev):
+    """The library's own communicator (NCCL loaded by libvitb200.so); torch.distributed only carries the 128-byte id."""
+    idt = torch.zeros(V.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(V.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, src=0)
+    return V.Comm(world, rank, bytes(idt.cpu().numpy().tobytes()), local)
+
+
+def reduce_max(torch, dist, dev, x, world):
+    if world == 1:
+        return x
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(torch, dist, dev, x, world):
+    if world == 1:
+        return x
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def run_config5(args, V, torch, dist, rank, world, local, dev):
+    """BASELINE.json configs[4]: --streams (default 1024) independent 256-Mbit s8 streams, int16x2 core, sharded over the
+    ranks in contiguous blocks, generated per batch on the device, decoded --wave streams per launch, the packed output
+    bits gathered to rank 0 per finished wave (vit_job_run, csrc/vit_mg.cu).  STRONG scaling: the job is fixed."""
+    options, n_bits, snr = WORKLOADS[args.workload]
+    nstreams = args.streams if args.streams > 1 else 1024
+    comm = make_comm(V, torch, dist, world, rank, local, dev) if world > 1 else None
+    mode = V.GATHER_MODES[args.gather]
+    passes = {}
+    checks = {}
+    for name, m in (("with_gather", mode), ("without_gather", V.GATHER_NONE)):
+        if name == "with_gather" and mode == V.GATHER_NONE:
+            continue
+        job = V.StreamJob(comm, local, options=options, n_bits=n_bits, nstreams=nstreams, wave=args.wave, batch=args.batch, seed=1,
+                          source=V.SOURCE_PRBS31, amp=HARNESS_SCALE, sigma=10.0 ** (-snr / 5.0), gather=m, root=0)
+        with ClockSampler(local) as cs:
+            cs.mark()
+            r = job.run()
+            cs.unmark()
+        errs = job.stream_errors()
+        r["job_ms_max"] = reduce_max(torch, dist, dev, r["job_ms"], world)
+        r["decode_ms_max"] = reduce_max(torch, dist, dev, r["decode_ms"], world)
+        r["bits_total"] = reduce_sum(torch, dist, dev, float(r["decoded_bits"]), world)
+        r["errors_total"] = reduce_sum(torch, dist, dev, float(r["bit_errors"]), world)
+        r["worst_stream_errors"] = reduce_max(torch, dist, dev, float(max(errs) if errs else 0), world)
+        r["launches_total"] = reduce_sum(torch, dist, dev, float(r["launches"]), world)
+        r["clocks"] = cs.summary()
+        passes[name] = r
+        if name == "with_gather" and rank == 0:
+            # oracle slices of two streams of EVERY rank's block, read from the gathered buffer on the root
+            from oracle import oracle as O
+            gptr, stride = job.gathered()
+            N = 2 * n_bits
+            bpp = 16 if options & 0x100 else 32
+            ok, checked = True, []
+            for p in range(world):
+                first, count = V.shard_range(nstreams, world, p)
+                for s in sorted({first, first + count - 1}):
+                    buf, _ = make_stream_device(V, torch, n_bits, options & 0xF, snr, 1 + s, dev)
+                    for sa, sb in ((0, 2), (6398, 6400)):
+                        b0, nb, w0, nw = O.segment_window(options, N, sa, sb)
+                        _, exp = O.decode_window(options, buf[b0:b0 + nb].cpu().numpy(), N, sa, sb)
+                        got = V.dev_to_host(gptr + s * stride + w0 * (bpp // 8), nw * (bpp // 8)).view(exp.dtype)
+                        ok = ok and bool(np.array_equal(got, exp))
+                    checked.append(s)
+                    del buf
+            checks = {"oracle_slices_equal": ok, "streams_checked": checked}
+        job.close()
+    if rank == 0:
+        main_pass = passes.get("with_gather", passes["without_gather"])
+        wo = passes["without_gather"]
+        bits = main_pass["bits_total"]
+        _, sm_max_mhz, _ = measured_peaks()
+        peak = N_SM * 4 * sm_max_mhz * 1e6 / 3 / 1e9
+        k_gbps = bits / world / (wo["decode_ms_max"] * 1e6)       # per GPU, decode launches only
+        line = {
+            "metric": "decoded Gb/s", "value": bits / (main_pass["job_ms_max"] * 1e6), "unit": "Gb/s", "n_gpus": world, "steps": 1, "warmup": 0,
+            "ms_per_step": main_pass["job_ms_max"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16x2",
+            "data": "synthetic",
+            "value_without_gather": wo["bits_total"] / (wo["job_ms_max"] * 1e6),
+            "config": dict(workload_config(args.workload, options, n_bits, snr, world), streams=nstreams, wave=args.wave, batch=args.batch,
+                           gather=args.gather, nccl_version=V.lib().vit_comm_nccl_version() if world > 1 else None,
+                           sharding="contiguous blocks of %d streams per GPU, one decoder per GPU, packed output bits gathered to rank 0 per finished wave" % (nstreams // world),
+                           timing="device events per batch round: first decode launch -> end of the round's last gather, summed; max over ranks; generation untimed"),
+            "gpu_launches": int(main_pass["launches_total"]), "clocks": main_pass["clocks"],
+            "check": dict(checks, bit_errors=int(main_pass["errors_total"]), ber=main_pass["errors_total"] / bits,
+                          worst_stream_bit_errors=int(main_pass["worst_stream_errors"])),
+            "passes": {k: {kk: v[kk] for kk in ("job_ms_max", "decode_ms_max", "synth_ms", "bits_total", "errors_total")} for k, v in passes.items()},
+            "roofline": {"bound": "issue", "achieved": k_gbps, "peak": peak, "unit": "Gb/s decoded per GPU", "frac": k_gbps / peak,
+                         "how": "per-GPU decode rate of the multi-stream launches against the ACS-op issue roofline (3 warp-instructions per decoded bit)", "traffic": None},
+            "e2e": None,
+        }
+        print(json.dumps(line))
+    if comm is not None:
+        comm.close()
 
 
 def main():
@@ -325,7 +397,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s4_b16_o32_32M", choices=sorted(WORKLOADS))
-    ap.add_argument("--streams", type=int, default=1, help="independent codeword streams decoded per step by ONE launch (config 5 shape)")
+    ap.add_argument("--streams", type=int, default=1, help="independent codeword streams decoded per step by ONE launch; config5: streams of the whole job (default 1024)")
+    ap.add_argument("--gather", default=None, choices=["nccl", "copy", "direct", "none"],
+                    help="N > 1: how the packed output bits reach rank 0 (default: nccl for config5, copy for the per-step bench)")
+    ap.add_argument("--wave", type=int, default=16, help="config5: streams per decode launch")
+    ap.add_argument("--batch", type=int, default=32, help="config5: streams generated ahead of each timed decode phase")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -349,6 +425,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     V = load_pkg()
+    if args.workload == "config5":
+        args.gather = args.gather or "nccl"
+        run_config5(args, V, torch, dist, rank, world, local, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    args.gather = args.gather or DEFAULT_STEP_GATHER
     it, bpp = options & 0xF, (16 if options & 0x100 else 32)
     dec = V.ViterbiCUDA(options, 2 * n_bits, device=local)
     N = 2 * n_bits
@@ -357,86 +440,122 @@ def main():
 
     # distinct input streams rotated step to step so that the working set exceeds L2 (126 MB)
     S = max(1, args.streams)
-    in_stride = (in_bytes + 255) // 256 * 256
+    in_stride = (in_bytes + 4 + 255) // 256 * 256
     nbuf = max(2, min(8, int(300e6 // (in_bytes * S)) + 1)) if in_bytes * S < 300e6 else 1
+    seed0 = 1 + 1000 * rank
     streams = []
     for k in range(nbuf):
-        parts, bits0 = [], None
+        buf = torch.zeros(S * in_stride, dtype=torch.uint8, device=dev)
         for j in range(S):
-            bits, packed, _ = make_stream_device(torch, n_bits, it, snr, 1000 * rank + k * S + j + 1, dev)
-            pad = in_stride - packed.numel()
-            if pad:
-                packed = torch.cat([packed, torch.zeros(pad, dtype=torch.uint8, device=dev)])
-            parts.append(packed)
-            if k == 0 and j == 0:
-                bits0 = bits
-        streams.append((bits0, torch.cat(parts) if S > 1 else parts[0]))
-    # Outputs go to a ring of 2 x GB slots.  For N > 1 the packed output bits of GB consecutive steps are
-    # gathered with ONE NCCL all_gather_into_tensor (flat buffers, no staging copies) that runs asynchronously
-    # while the next GB decodes fill the other half of the ring: the collective is latency-bound at this size,
-    # so it is batched, and it never sits on the decode stream's critical path.
+            packed, _ = make_stream_device(V, torch, n_bits, it, snr, seed0 + k * S + j, dev)
+            buf[j * in_stride:j * in_stride + in_bytes] = packed[:in_bytes]
+            del packed
+        streams.append(buf)
+    torch.cuda.synchronize()
+
+    # Outputs go to a ring of 2 x GB slots per rank.  For N > 1 the packed output bits are gathered to rank 0 with the
+    # library's own gather (vit_comm_gatherv, csrc/vit_mg.cu) on its own high-priority stream while the next decodes run:
+    #   copy   one device-to-device copy per step into rank 0's buffer (copy engines over NVLink, no SM used)
+    #   nccl   one grouped ncclSend/ncclRecv per GB steps (NCCL kernels beside the decode kernel)
+    #   direct the decode kernel stores its packs straight into rank 0's buffer over NVLink
     GB = 8 if world > 1 else 1
     out_stride1 = (out_bytes + 255) // 256 * 256          # per stream
     out_stride = out_stride1 * S                            # per step
-    ring = torch.zeros(2 * GB * out_stride, dtype=torch.uint8, device=dev)
-    d_out = ring[:out_stride]
-    gathered = [torch.empty(world * GB * out_stride, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
-    pending = [None, None]
+    ring_bytes = 2 * GB * out_stride
+    ring = torch.zeros(ring_bytes, dtype=torch.uint8, device=dev)
+    comm = make_comm(V, torch, dist, world, rank, local, dev) if world > 1 else None
+    root_buf = comm.shared_alloc(world * ring_bytes, 0) if comm is not None else None
     st = torch.cuda.current_stream()
+    state = {"gather": V.GATHER_MODES[args.gather] if world > 1 else V.GATHER_NONE}
 
-    def gather_half(h):
-        pending[h] = dist.all_gather_into_tensor(gathered[h], ring[h * GB * out_stride:(h + 1) * GB * out_stride], async_op=True)
+    def out_ptr(slot):
+        if state["gather"] == V.GATHER_DIRECT:
+            return root_buf + rank * ring_bytes + slot * out_stride      # rank 0's buffer, mapped into this process
+        return ring.data_ptr() + slot * out_stride
+
+    def gather_slots(slot0, nslots):
+        offs = [p * ring_bytes + slot0 * out_stride for p in range(world)]
+        comm.gatherv(state["gather"], ring.data_ptr() + slot0 * out_stride, root_buf, offs, [nslots * out_stride] * world, 0, st.cuda_stream)
 
     def step(k):
         slot = k % (2 * GB)
-        h = slot // GB
-        if slot % GB == 0 and pending[h] is not None:
-            pending[h].wait()              # stream-side wait: this half of the ring is free again
-            pending[h] = None
-        dec.run_device(streams[k % nbuf][1].data_ptr(), ring[slot * out_stride:].data_ptr(), N, stream=st.cuda_stream,
+        if comm is not None and slot % GB == 0 and state["gather"] in (V.GATHER_NCCL, V.GATHER_COPY):
+            comm.stream_wait(st.cuda_stream)   # the gathers that read this half of the ring were issued 2*GB steps ago
+        dec.run_device(streams[k % nbuf].data_ptr(), out_ptr(slot), N, stream=st.cuda_stream,
                        nstreams=S, in_stride=in_stride, out_stride=out_stride1)
-        if world > 1 and slot % GB == GB - 1:
-            gather_half(h)                 # NCCL over NVLink: packed output bits only
+        if state["gather"] == V.GATHER_COPY:
+            gather_slots(slot, 1)
+        elif state["gather"] == V.GATHER_NCCL and slot % GB == GB - 1:
+            gather_slots(slot - GB + 1, GB)
+
+    def flush_partial(last_k):
+        if state["gather"] == V.GATHER_NCCL and (last_k % GB) != GB - 1:
+            slot = last_k % (2 * GB)
+            gather_slots(slot - slot % GB, slot % GB + 1)                # partial group at the end of a run
 
     def drain(last_k=None):
-        if world > 1 and last_k is not None and (last_k % GB) != GB - 1:
-            gather_half((last_k % (2 * GB)) // GB)      # partial group at the end of the run
-        for h in (0, 1):
-            if pending[h] is not None:
-                pending[h].wait()
-                pending[h] = None
+        if last_k is not None:
+            flush_partial(last_k)
+        if comm is not None:
+            st.synchronize()
+            comm.barrier()                     # every rank's gathers have landed in rank 0's buffer
+
+    def timed(steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(st)
+        for k in range(steps):
+            step(k)
+        flush_partial(steps - 1)
+        if comm is not None and state["gather"] in (V.GATHER_NCCL, V.GATHER_COPY):
+            comm.stream_wait(st.cuda_stream)   # the timed region ends when this rank's gathers have completed
+        e1.record(st)
+        drain()                                # host-waits for this rank, then meets the other ranks
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), wall_ms
 
     # correctness gate inside the bench: BER == 0 at this SNR, and a slice equals the golden model
     step(0)
     drain(0)
     torch.cuda.synchronize()
-    errs = count_errors_device(torch, d_out, streams[0][0], M, bpp)
+    gathering = comm is not None and state["gather"] != V.GATHER_NONE
+    # rank 0 checks what arrived in the gathered buffer; a sender checks its local packs (or, with direct stores, its
+    # block of rank 0's buffer through the mapping)
+    first_out = ring.data_ptr()
+    if gathering and (rank == 0 or state["gather"] == V.GATHER_DIRECT):
+        first_out = root_buf + rank * ring_bytes
+    errs = V.count_errors_synth_device(options, first_out, M, seed=seed0, source=V.SOURCE_PRBS31)
     check = {"bit_errors": errs, "ber": errs / M}
     if rank == 0:
         from oracle import oracle as O
-        host_in = streams[0][1][:in_bytes].cpu().numpy()   # stream 0 of the step
+        host_in = streams[0][:in_bytes].cpu().numpy()   # stream 0 of the step
         seg = O.decode(options, host_in, N, segs=(1000, 1016))
         P = M // bpp
         q, r = divmod(P, 6400)
         a, b = q * 1000 + min(1000, r), q * 1016 + min(1016, r)
-        got = d_out[:out_bytes].cpu().numpy().view(np.uint16 if bpp == 16 else np.uint32)
+        got = V.dev_to_host(first_out, out_bytes).view(np.uint16 if bpp == 16 else np.uint32)
         check["oracle_slice_equal"] = bool(np.array_equal(got[a:b], seg[a:b]))
+        if comm is not None and state["gather"] != V.GATHER_NONE:
+            # what the other ranks sent: the last rank's first stream, regenerated here and decoded by the golden model
+            pl, _ = make_stream_device(V, torch, n_bits, it, snr, 1 + 1000 * (world - 1), dev)
+            seg = O.decode(options, pl[:in_bytes].cpu().numpy(), N, segs=(1000, 1016))
+            got = V.dev_to_host(root_buf + (world - 1) * ring_bytes, out_bytes).view(np.uint16 if bpp == 16 else np.uint32)
+            check["gathered_slice_of_last_rank_equal"] = bool(np.array_equal(got[a:b], seg[a:b]))
+            del pl
 
     for k in range(args.warmup):
         step(k)
     drain(args.warmup - 1)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = dec.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as cs:
         # same kernels again, for about 0.3 s: NVML answers a clock query in milliseconds to tens of milliseconds,
         # so a short timed region alone may hold few samples; the sampler sees this identical load as well.
         # The step count is derived from the workload size only, NOT from a clock: every rank must run the same number
-        # of steps, because step() issues the NCCL gathers (a clock-driven loop count differs between ranks and
-        # desynchronises the collectives).
+        # of steps, because step() issues the gathers.
         est_step_s = M * S / 80e9
         n_load = max(args.warmup, min(2000, int(0.3 / est_step_s) + 1))
         for k in range(n_load):
@@ -444,77 +563,58 @@ def main():
             if (k + 1) % 64 == 0:
                 st.synchronize()
         drain(n_load - 1)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
         launches0 = dec.launch_count()
         cs.mark()
-        e0.record(st)
-        for k in range(args.steps):
-            step(k)
-        drain(args.steps - 1)
-        e1.record(st)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ms_dev, ms_wall = timed(args.steps)
         cs.unmark()
-        ms_total = e0.elapsed_time(e1)
+        launches = dec.launch_count() - launches0
+        ms_total = reduce_max(torch, dist, dev, ms_dev, world)
+        ms_wall_max = reduce_max(torch, dist, dev, ms_wall, world)
+        ms_nogather = None
+        if world > 1 and state["gather"] != V.GATHER_NONE:
+            keep = state["gather"]
+            state["gather"] = V.GATHER_NONE
+            nd, _ = timed(args.steps)
+            ms_nogather = reduce_max(torch, dist, dev, nd, world)
+            state["gather"] = keep
         # kernel-only duration for the roofline: events bracketing the launch on the launch stream
         kms = []
         for k in range(min(args.steps, 20)):
-            kms.append(dec.run_device(streams[k % nbuf][1].data_ptr(), ring.data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True,
+            kms.append(dec.run_device(streams[k % nbuf].data_ptr(), ring.data_ptr(), N, stream=st.cuda_stream, want_kernel_time=True,
                                       nstreams=S, in_stride=in_stride, out_stride=out_stride1))
-    launches = dec.launch_count() - launches0 - len(kms)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = M * S * world / (ms_step * 1e6)                   # whole-job decoded Gb/s
     kernel_ms = statistics.mean(kms)
 
-    # e2e through the public host-buffer call (pinned host memory), copies inside the timed region
+    # e2e through the public host-buffer call, copies inside the timed region: pinned buffers, and pageable ones
     e2e = None
     if not args.no_e2e and in_bytes < 8e9 and S == 1:
-        h_in = [s[1][:in_bytes].cpu().pin_memory() for s in streams[:min(nbuf, 4)]]
+        h_in = [s[:in_bytes].cpu().pin_memory() for s in streams[:min(nbuf, 4)]]
         h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
         h_out_np = h_out.numpy().view(dec.decPack_t)
         h_in_np = [h.numpy() for h in h_in]
-        for k in range(3):
-            dec.run(h_in_np[k % len(h_in_np)], N, output_h=h_out_np)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            dec.run(h_in_np[k % len(h_in_np)], N, output_h=h_out_np)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+
+        def e2e_leg(bufs_in, buf_out, steps):
+            for k in range(3):
+                dec.run(bufs_in[k % len(bufs_in)], N, output_h=buf_out)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for k in range(steps):
+                dec.run(bufs_in[k % len(bufs_in)], N, output_h=buf_out)
+            return reduce_max(torch, dist, dev, time.perf_counter() - t0, world)
+        dt = e2e_leg(h_in_np, h_out_np, args.steps)
         e2e = {"value": M * world * args.steps / dt / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": int(in_bytes),
                "d2h_bytes_per_step": int(out_bytes), "host_memory": "pinned", "timer": "host wall clock around the synchronous call"}
         # the same call from PAGEABLE numpy buffers -- the reference's calling convention (std::vector storage,
         # viterbiDF.h:188-193) and what the reference arm's e2e is measured with
-        p_in = [np.array(h, copy=True) for h in h_in_np[:2]]
+        p_in = [np.array(h, copy=True) for h in h_in_np[:3]]
         p_out = np.empty(out_bytes // np.dtype(dec.decPack_t).itemsize, dec.decPack_t)
-        for k in range(3):
-            dec.run(p_in[k % len(p_in)], N, output_h=p_out)
-        if world > 1:
-            dist.barrier()
         n_pg = max(3, args.steps // 2)
-        t0 = time.perf_counter()
-        for k in range(n_pg):
-            dec.run(p_in[k % len(p_in)], N, output_h=p_out)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = e2e_leg(p_in, p_out, n_pg)
         e2e["pageable"] = {"value": M * world * n_pg / dt / 1e9, "unit": "Gb/s", "steps": n_pg, "host_memory": "pageable (numpy)",
-                           "how": "staged through the handle's pinned buffers by worker threads, time-sliced upload"}
+                           "how": "staged through the handle's pinned buffers by worker threads, time-sliced upload (csrc/vit_api.cu run_gated)"}
+        assert np.array_equal(p_out, h_out_np)
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_kind = measured_peaks()
@@ -526,13 +626,17 @@ def main():
         k_gbps = M * S / (kernel_ms * 1e6)
         alg_bytes = M * S * (BYTES_PER_BIT_IN[it] + 0.125)
         info = dec.kernel_info()
+        traffic = NCU_DRAM_BYTES.get((args.workload, S))
+        cfg = workload_config(args.workload, options, n_bits, snr, world)
+        run_info = {"streams_per_step_per_gpu": S, "l2": "inputs rotate over %d distinct device buffers (%.0f MB > 126 MB L2)" % (nbuf, nbuf * in_bytes * S / 1e6),
+                    "timed_region_ms": ms_total,
+                    "note": "a step is one 32-Mbit decode (~0.33 ms): K steps are a short timed region; the NVML sampler also covers an identical ~0.3 s load phase before it",
+                    "gather": ("vit_comm_gatherv mode '%s' on its own stream, overlapped with the following decodes; the timed region ends when this rank's gathers have completed" % args.gather) if world > 1 else None}
         line = {
             "metric": "decoded Gb/s", "value": value, "unit": "Gb/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0x00: "int32", 0x10: "int16x2", 0x20: "f16x2"}[options & 0xF0], "data": "synthetic",
-            "config": {"workload": args.workload, "message_bits": n_bits, "options": "0x%03x" % options, "snr_db": snr,
-                       "segments": 6400, "streams_per_step_per_gpu": S, "l2": "inputs rotate over %d distinct device buffers (%.0f MB > 126 MB L2)" % (nbuf, nbuf * in_bytes / 1e6),
-                       "parallelism": ("stream-sharded x%d, one NCCL all_gather_into_tensor of packed output bits per %d steps, overlapped" % (world, GB)) if world > 1 else "single GPU"},
+            "config": cfg, "run_info": run_info,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
             "kernel": {"ms": kernel_ms, "gbps": k_gbps, "regs": info["regs"], "smem_bytes": info["smem_bytes"],
                        "grid": [1600, S, 1], "block": 32},
@@ -540,15 +644,21 @@ def main():
                          "peak_at_measured_clock": issue_peak_at_clock, "frac_at_measured_clock": k_gbps / issue_peak_at_clock,
                          "achieved_acs_warp_inst_per_s": k_gbps * 1e9 * wi_per_bit, "peak_warp_inst_per_s": N_SM * 4 * sm_max_mhz * 1e6,
                          "how": "ACS-op roofline: 192 add/compare-select ops per decoded bit = %d warp-instructions; peak = 148 SM x 4 issue/clk x f_SM / that" % wi_per_bit,
-                         "traffic": NCU_DRAM_BYTES.get((args.workload, S)), "traffic_source": "profiles/r1_v7_ncu_core_0x011.txt (dram__bytes_read+write per launch, one ncu --set full capture)" if NCU_DRAM_BYTES.get((args.workload, S)) else None},
+                         "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kernel_ms * 1e6), "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / (kernel_ms * 1e6) / hbm_peak, "peak_kind": peak_kind, "traffic": NCU_DRAM_BYTES.get((args.workload, S)),
+                             "frac": alg_bytes / (kernel_ms * 1e6) / hbm_peak, "peak_kind": peak_kind, "traffic": traffic[0] if traffic else None,
                              "algorithmic_bytes_per_launch": alg_bytes},
         }
+        if world > 1:
+            line["value_without_gather"] = M * S * world * args.steps / (ms_nogather * 1e6) if ms_nogather else value
+            line["gather"] = {"mode": args.gather, "wall_ms_incl_gather_tail": ms_wall_max,
+                              "value_by_wall_clock": M * S * world * args.steps / (ms_wall_max * 1e6)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(options, n_bits, snr)
         print(json.dumps(line))
     dec.close()
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

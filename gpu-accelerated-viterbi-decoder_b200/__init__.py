@@ -32,6 +32,23 @@ class ViterbiError(RuntimeError):
     pass
 
 
+GATHER_NONE, GATHER_NCCL, GATHER_COPY, GATHER_DIRECT = 0, 1, 2, 3
+GATHER_MODES = {"none": GATHER_NONE, "nccl": GATHER_NCCL, "copy": GATHER_COPY, "direct": GATHER_DIRECT}
+COMM_ID_BYTES = 128
+
+
+class JobConfig(C.Structure):
+    """vit_job_config (include/vit_b200.h)"""
+    _fields_ = [("options", C.c_int), ("n_bits", C.c_size_t), ("nstreams", C.c_uint), ("wave", C.c_uint), ("batch", C.c_uint),
+                ("seed", C.c_uint), ("source", C.c_int), ("amp", C.c_int), ("sigma", C.c_double), ("gather", C.c_int), ("root", C.c_int)]
+
+
+class JobResult(C.Structure):
+    """vit_job_result (include/vit_b200.h)"""
+    _fields_ = [("decode_ms", C.c_double), ("job_ms", C.c_double), ("synth_ms", C.c_double), ("decoded_bits", C.c_ulonglong),
+                ("bit_errors", C.c_ulonglong), ("max_stream_errors", C.c_ulonglong), ("launches", C.c_ulonglong), ("streams", C.c_uint)]
+
+
 _lib = None
 
 
@@ -76,6 +93,31 @@ def lib():
         L.vit_synth_device_ex.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp, vp]
         L.vit_count_errors_synth_device.restype = C.c_int
         L.vit_count_errors_synth_device.argtypes = [C.c_int, vp, sz, C.c_uint, C.c_int, C.POINTER(C.c_ulonglong), vp]
+        L.vit_dev_set.restype, L.vit_dev_set.argtypes = C.c_int, [C.c_int]
+        L.vit_dev_copy_to_host.restype, L.vit_dev_copy_to_host.argtypes = C.c_int, [vp, vp, sz]
+        L.vit_dev_copy_from_host.restype, L.vit_dev_copy_from_host.argtypes = C.c_int, [vp, vp, sz]
+        L.vit_comm_available.restype, L.vit_comm_available.argtypes = C.c_int, []
+        L.vit_comm_nccl_version.restype, L.vit_comm_nccl_version.argtypes = C.c_int, []
+        L.vit_comm_get_unique_id.restype, L.vit_comm_get_unique_id.argtypes = C.c_int, [vp]
+        L.vit_comm_init_rank.restype, L.vit_comm_init_rank.argtypes = C.c_int, [C.POINTER(vp), C.c_int, C.c_int, vp, C.c_int]
+        L.vit_comm_init_all.restype, L.vit_comm_init_all.argtypes = C.c_int, [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]
+        L.vit_comm_destroy.restype, L.vit_comm_destroy.argtypes = None, [vp]
+        L.vit_comm_rank.restype, L.vit_comm_rank.argtypes = C.c_int, [vp]
+        L.vit_comm_size.restype, L.vit_comm_size.argtypes = C.c_int, [vp]
+        L.vit_comm_barrier.restype, L.vit_comm_barrier.argtypes = C.c_int, [vp]
+        L.vit_comm_stream_wait.restype, L.vit_comm_stream_wait.argtypes = C.c_int, [vp, vp]
+        L.vit_comm_stream.restype, L.vit_comm_stream.argtypes = vp, [vp]
+        L.vit_shard_range.restype, L.vit_shard_range.argtypes = None, [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+        L.vit_shard_owner.restype, L.vit_shard_owner.argtypes = C.c_int, [sz, C.c_int, sz]
+        L.vit_comm_shared_alloc.restype, L.vit_comm_shared_alloc.argtypes = C.c_int, [vp, C.POINTER(vp), sz, C.c_int]
+        L.vit_comm_gatherv.restype = C.c_int
+        L.vit_comm_gatherv.argtypes = [vp, C.c_int, vp, vp, C.POINTER(sz), C.POINTER(sz), C.c_int, vp]
+        L.vit_job_create.restype, L.vit_job_create.argtypes = C.c_int, [C.POINTER(vp), vp, C.c_int, C.POINTER(JobConfig)]
+        L.vit_job_run.restype, L.vit_job_run.argtypes = C.c_int, [vp, C.POINTER(JobResult)]
+        L.vit_job_gathered.restype, L.vit_job_gathered.argtypes = vp, [vp, C.POINTER(sz)]
+        L.vit_job_stream_range.restype, L.vit_job_stream_range.argtypes = C.c_int, [vp, C.POINTER(sz), C.POINTER(sz)]
+        L.vit_job_stream_errors.restype, L.vit_job_stream_errors.argtypes = C.c_int, [vp, C.POINTER(C.c_ulonglong), sz]
+        L.vit_job_destroy.restype, L.vit_job_destroy.argtypes = None, [vp]
         _lib = L
     return _lib
 
@@ -206,3 +248,98 @@ class ViterbiCUDA:
 
     def set_segments(self, segments):
         _check(lib().vit_set_segments(self._h, segments))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU: stream sharding + gather of the packed output bits (C ABI vit_comm_* / vit_job_*, csrc/vit_mg.cu)
+
+def dev_to_host(src_ptr, nbytes):
+    """nbytes of device memory at src_ptr as a numpy uint8 array (synchronous copy)."""
+    out = np.empty(int(nbytes), np.uint8)
+    _check(lib().vit_dev_copy_to_host(out.ctypes.data, src_ptr, int(nbytes)))
+    return out
+
+
+def shard_range(nstreams, nranks, rank):
+    """(first, count): the contiguous block of streams rank owns (vit_shard_range)."""
+    a, b = C.c_size_t(0), C.c_size_t(0)
+    lib().vit_shard_range(int(nstreams), int(nranks), int(rank), C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def shard_owner(nstreams, nranks, stream):
+    return int(lib().vit_shard_owner(int(nstreams), int(nranks), int(stream)))
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().vit_comm_get_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """One rank of an N-GPU communicator (NCCL underneath, loaded at run time)."""
+
+    def __init__(self, nranks, rank, unique_id, device):
+        self._c = C.c_void_p()
+        idb = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        _check(lib().vit_comm_init_rank(C.byref(self._c), int(nranks), int(rank), idb, int(device)))
+        self.rank, self.nranks, self.device = int(rank), int(nranks), int(device)
+
+    def barrier(self):
+        _check(lib().vit_comm_barrier(self._c))
+
+    def stream_wait(self, stream):
+        _check(lib().vit_comm_stream_wait(self._c, stream))
+
+    def shared_alloc(self, nbytes, root=0):
+        p = C.c_void_p()
+        _check(lib().vit_comm_shared_alloc(self._c, C.byref(p), int(nbytes), int(root)))
+        return p.value
+
+    def gatherv(self, mode, send_ptr, recv_base, offsets, sizes, root=0, producer_stream=0):
+        n = self.nranks
+        off = (C.c_size_t * n)(*[int(x) for x in offsets])
+        siz = (C.c_size_t * n)(*[int(x) for x in sizes])
+        _check(lib().vit_comm_gatherv(self._c, int(mode), send_ptr, recv_base, off, siz, int(root), producer_stream))
+
+    def close(self):
+        if getattr(self, "_c", None) and _lib is not None:
+            _lib.vit_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+
+class StreamJob:
+    """The sharded stream job (vit_job_*): nstreams independent streams generated, decoded and gathered on the GPUs."""
+
+    def __init__(self, comm, device, **cfg):
+        self.cfg = JobConfig(**cfg)
+        self._j = C.c_void_p()
+        self._comm = comm
+        _check(lib().vit_job_create(C.byref(self._j), comm._c if comm is not None else None, int(device), C.byref(self.cfg)))
+
+    def run(self):
+        r = JobResult()
+        _check(lib().vit_job_run(self._j, C.byref(r)))
+        return {k: getattr(r, k) for k, _ in JobResult._fields_}
+
+    def gathered(self):
+        st = C.c_size_t(0)
+        p = lib().vit_job_gathered(self._j, C.byref(st))
+        return p, int(st.value)
+
+    def stream_range(self):
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        _check(lib().vit_job_stream_range(self._j, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def stream_errors(self):
+        first, count = self.stream_range()
+        arr = (C.c_ulonglong * max(count, 1))()
+        _check(lib().vit_job_stream_errors(self._j, arr, count))
+        return [int(arr[i]) for i in range(count)]
+
+    def close(self):
+        if getattr(self, "_j", None) and _lib is not None:
+            _lib.vit_job_destroy(self._j)
+            self._j = C.c_void_p()

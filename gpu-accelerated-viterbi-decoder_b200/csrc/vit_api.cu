@@ -38,6 +38,13 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+}  // namespace
+// shared with the other translation units of the library (vit_mg.cu); not exported
+int vit_set_error(int code, const char* msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+namespace {
 #define VIT_CUDA(call)                                                                             \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -61,6 +68,42 @@ struct DeviceGuard {
     ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
 };
 #define VIT_ON_DEVICE(h) DeviceGuard guard_; VIT_CUDA(guard_.enter((h)->device))
+
+// Copy into a pinned staging buffer with non-temporal stores: the destination is read next by the GPU's DMA engine, not
+// by this core, so write-allocating its cache lines (what a plain memcpy of a few KB does) only adds memory traffic.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) void stream_copy_avx2(char* dst, const char* src, size_t n) {
+    const size_t head = std::min(n, (size_t)((32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31));
+    if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+    }
+    for (; i + 32 <= n; i += 32)
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)));
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+#endif
+void stage_copy(char* dst, const char* src, size_t n) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && getenv("VIT_STAGE_PLAIN_MEMCPY") == nullptr;
+    if (avx2 && n >= 256) { stream_copy_avx2(dst, src, n); return; }
+#endif
+    memcpy(dst, src, n);
+}
+void stage_fence() {
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+}
 
 // Worker threads that copy pageable host memory into the pinned staging buffers (vit_run with pageable buffers).
 // The workers sleep between calls and spin between the jobs of one call (a condition-variable wake-up per column block
@@ -345,7 +388,7 @@ int ensure_staging(vit_handle* h, size_t in_bytes, size_t out_bytes) {
     }
     if (!h->pool) {
         const char* e = getenv("VIT_STAGE_THREADS");
-        int n = e ? atoi(e) : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        int n = e ? atoi(e) : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
         n = std::max(1, std::min(n, 64));
         h->pool = new (std::nothrow) StagePool(n - 1);
         if (!h->pool) return fail(VIT_ERR_ARG, "out of host memory");
@@ -367,7 +410,8 @@ int run_gated(vit_handle* h, const HostRun& g, bool stage_in, bool stage_out, bo
     GatePlan gp;
     if (stage_in) {
         // equal column blocks: the staging copy of block b+1 hides behind the upload of block b
-        gp.n = (unsigned)std::min<size_t>(8, std::max<size_t>(2, g.nsuper / 4));
+        static const int env_blocks = [] { const char* e = getenv("VIT_STAGE_BLOCKS"); return e ? atoi(e) : 0; }();   // measurement hook
+        gp.n = (unsigned)std::min<size_t>(env_blocks > 0 ? (size_t)std::min(env_blocks, 8) : 4, std::max<size_t>(2, g.nsuper / 4));
         for (unsigned b = 0; b < gp.n; b++) gp.super[b] = (unsigned)(g.nsuper * b / gp.n);
     } else {
         // column blocks of 1/2, 3/8 and 1/8 of a segment (profiles/r1_upload_pattern_probe.txt): fewer, wider strided
@@ -407,6 +451,7 @@ int run_gated(vit_handle* h, const HostRun& g, bool stage_in, bool stage_out, bo
         VIT_CUDA(cudaMemcpyAsync(dst + body_end, src + body_end, g.in_bytes - body_end, cudaMemcpyHostToDevice, h->copy_stream));
     }
     static const bool lose_gate = getenv("VIT_TEST_LOSE_GATE") != nullptr;           // test hook: never open the last gate
+    double t_stage = 0.0;
     for (unsigned b = 0; b < gp.n; b++) {
         // columns [lo, hi) of every segment row: super-steps [super[b], super[b+1]) plus the read-ahead the kernel's
         // 16-byte staging pieces take (<= 15 bytes before, <= 27 bytes after)
@@ -420,10 +465,13 @@ int run_gated(vit_handle* h, const HostRun& g, bool stage_in, bool stage_out, bo
                 for (size_t w = gi * 32; w < std::min(g.W, gi * 32 + 32); w++) {
                     const size_t row = w < g.r ? w * pitch1 : grp2 + (w - g.r) * pitch2;
                     const size_t wd = w < g.r ? w1 : w2;
-                    if (wd > lo) memcpy(stage + row + lo, user + row + lo, wd - lo);
+                    if (wd > lo) stage_copy(stage + row + lo, user + row + lo, wd - lo);
                 }
+                stage_fence();
             };
+            const double ts = dbg ? now() : 0.0;
             h->pool->parallel_for(groups, job);
+            if (dbg) t_stage += now() - ts;
         }
         if (g.r && w1 > lo)
             VIT_CUDA(cudaMemcpy2DAsync(dst + lo, pitch1, src + lo, pitch1, w1 - lo, g.r, cudaMemcpyHostToDevice, h->copy_stream));
@@ -445,8 +493,8 @@ int run_gated(vit_handle* h, const HostRun& g, bool stage_in, bool stage_out, bo
         cudaEventSynchronize(h->ev_kdone);
         const double t_kernel = now();
         cudaStreamSynchronize(h->stream);
-        fprintf(stderr, "[vit_run gated%s] issue %.3f ms, upload done +%.3f, kernel done +%.3f, download done +%.3f\n",
-                staged ? " staged" : "", t_issued - t_begin, t_copy - t_begin, t_kernel - t_begin, now() - t_begin);
+        fprintf(stderr, "[vit_run gated%s] %u blocks, issue %.3f ms (staging copies %.3f), upload done +%.3f, kernel done +%.3f, download done +%.3f\n",
+                staged ? " staged" : "", gp.n, t_issued - t_begin, t_stage, t_copy - t_begin, t_kernel - t_begin, now() - t_begin);
     }
     cudaError_t e = cudaStreamSynchronize(h->copy_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

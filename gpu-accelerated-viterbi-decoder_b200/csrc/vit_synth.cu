@@ -269,6 +269,9 @@ int vit_count_errors_device(int options, const void* out_d, const void* bits_d, 
 // plain device-memory helpers so that host-only callers (no CUDA headers) can use the device-resident entry points
 int vit_dev_alloc(void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes ? bytes : 1) == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
 void vit_dev_free(void* ptr) { if (ptr) cudaFree(ptr); }
+int vit_dev_copy_to_host(void* dst_h, const void* src_d, size_t bytes) { return cudaMemcpy(dst_h, src_d, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
+int vit_dev_copy_from_host(void* dst_d, const void* src_h, size_t bytes) { return cudaMemcpy(dst_d, src_h, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
+int vit_dev_set(int device) { return cudaSetDevice(device) == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
 int vit_dev_sync(void) { return cudaDeviceSynchronize() == cudaSuccess ? VIT_OK : VIT_ERR_CUDA; }
 int vit_dev_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 // page-locked host memory for callers without CUDA headers: vit_run takes its time-sliced upload path from such buffers

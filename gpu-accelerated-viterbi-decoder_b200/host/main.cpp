@@ -2,8 +2,11 @@
 // (reference src/main.cpp:14-264: -n/-s/-i/-m/-o/-c/-v/-h; sigma = 10^(-snr/5); quantiser scale 40000;
 // BER = mismatches / messageLen with decoded bit i compared to generated bit i+extraL).
 // Additions: reproducible seeds (--seed, --prbs), size_t message lengths, decoded Gb/s from device-side
-// kernel time, repeated timed runs (--reps) and multi-GPU stream sharding (--streams / --gpus: independent
-// codeword streams, one decoder per GPU, no stream is ever split).
+// kernel time, repeated timed runs (--reps), a device-side channel source (--device-source) and the multi-GPU
+// stream job (--streams S --gpus G [--gather nccl|copy|direct|none] [--wave W] [--batch B]): S independent
+// codeword streams of -n bits each, generated on the GPUs, sharded over G GPUs in contiguous blocks (one host
+// thread, one decoder and one communicator per GPU, no stream is ever split), the packed output bits gathered
+// to GPU 0 over NCCL / NVLink, timed on the device, with and without the gather (BASELINE.json configs[4]).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -26,6 +29,9 @@ struct Args {
     int streams = 1;
     int gpus = 1;
     bool deviceSource = false;      // generate, decode and count errors on the device (no host pipeline)
+    std::string gather = "nccl";    // how the stream job brings the packed output bits to GPU 0
+    int wave = 16;                  // streams per decode launch
+    int batch = 32;                 // streams generated ahead of each timed decode phase
 };
 
 static void usage(const char* prog) {
@@ -41,8 +47,13 @@ static void usage(const char* prog) {
               << "      --seed <integer>     Fixed seed for bits (noise uses seed+1); default: random_device.\n"
               << "      --prbs               PRBS-31 message bits instead of mt19937.\n"
               << "      --reps <integer>     Timed decoder runs (best kernel time is reported).\n"
-              << "      --streams <integer>  Independent copies of the stream to decode (sharded over --gpus).\n"
-              << "      --gpus <integer>     Number of GPUs (one decoder and one host thread per GPU).\n"
+              << "      --streams <integer>  Stream job: independent streams of -n bits, generated on the device,\n"
+              << "                           sharded over --gpus in contiguous blocks, outputs gathered to GPU 0.\n"
+              << "      --gpus <integer>     Number of GPUs (one decoder, one communicator and one host thread per GPU).\n"
+              << "      --gather <mode>      nccl (ncclSend/ncclRecv per finished wave, default) | copy (copy engines) |\n"
+              << "                           direct (the kernel stores into GPU 0's buffer over NVLink) | none.\n"
+              << "      --wave <integer>     Streams per decode launch (default 16).\n"
+              << "      --batch <integer>    Streams generated ahead of each timed decode phase (default 32).\n"
               << "      --device-source      Generate the channel, decode and count bit errors on the device\n"
               << "                           (counter-based source; needed for multi-Gbit -n, e.g. -n 4000000000 -i f).\n"
               << "  -h, --help               Display this help message.\n";
@@ -87,12 +98,15 @@ static Args parseArg(int argc, char* argv[]) {
         else if (f == "--reps") a.reps = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
         else if (f == "--streams") a.streams = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
         else if (f == "--gpus") a.gpus = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
+        else if (f == "--wave") a.wave = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
+        else if (f == "--batch") a.batch = std::max(1, number([](const std::string& s) { return std::stoi(s); }));
+        else if (f == "--gather") { a.gather = value(); lookup(f, a.gather, {{"nccl", 1}, {"copy", 2}, {"direct", 3}, {"none", 0}}); }
         else { std::cerr << "Error: Unknown or incomplete argument: " << f << std::endl; std::exit(1); }
     }
     return a;
 }
 
-struct Outcome { size_t ben = 0, decoded = 0; double best_ms = 0, box_gbps = 0; };
+struct Outcome { size_t ben = 0, decoded = 0; double best_ms = 0; };
 
 template <int options>
 Outcome runPipeline(const Args& a) {
@@ -127,34 +141,19 @@ Outcome runPipeline(const Args& a) {
     }
     out.best_ms = std::any_cast<float>(viterbi.getStatus("GPU kernel time"));
 
-    // timed repeats / multi-GPU stream sharding on the packed channel words of this stream
-    if (a.reps > 1 || a.streams > 1 || a.gpus > 1) {
+    // timed repeats on the packed channel words of this stream
+    if (a.reps > 1) {
         using encPack_t = typename Dec::encPack_t;
         Pipeline regen = front;   // same seeds -> same stream
         const auto packed = std::any_cast<std::vector<encPack_t>>(regen.run().final_output);
         const size_t inputNum = packed.size() * Dec::encDataPerPack;
-        std::vector<double> gpu_ms(a.gpus, 0.0);
-        std::vector<double> best(a.gpus, 1e30);
-        std::vector<std::thread> workers;
-        for (int g = 0; g < a.gpus; ++g)
-            workers.emplace_back([&, g] {
-                Dec dec(inputNum, g);
-                decVec_t o(dec.getOutputSize(inputNum) / sizeof(typename Dec::decPack_t));
-                for (int s = g; s < a.streams; s += a.gpus) {        // stream s -> GPU s mod G
-                    double b = 1e30;
-                    for (int r = 0; r < a.reps; ++r) {
-                        float ms = 0.f;
-                        dec.run(const_cast<encPack_t*>(packed.data()), o.data(), inputNum, &ms);
-                        b = std::min<double>(b, ms);
-                    }
-                    gpu_ms[g] += b;
-                    best[g] = std::min(best[g], b);
-                }
-            });
-        for (auto& w : workers) w.join();
-        out.best_ms = *std::min_element(best.begin(), best.end());
-        const double box_ms = *std::max_element(gpu_ms.begin(), gpu_ms.end());
-        out.box_gbps = static_cast<double>(out.decoded) * a.streams / (box_ms * 1e6);
+        Dec dec(inputNum, 0);
+        decVec_t o(dec.getOutputSize(inputNum) / sizeof(typename Dec::decPack_t));
+        for (int r = 0; r < a.reps; ++r) {
+            float ms = 0.f;
+            dec.run(const_cast<encPack_t*>(packed.data()), o.data(), inputNum, &ms);
+            out.best_ms = std::min<double>(out.best_ms, ms);
+        }
     }
     return out;
 }
@@ -193,6 +192,63 @@ Outcome runDevicePipeline(const Args& a) {
     return out;
 }
 
+// The multi-GPU stream job (BASELINE.json configs[4]): everything below the flags is the C ABI's vit_comm_* / vit_job_*
+// (csrc/vit_mg.cu); this harness only spawns one host thread per GPU and reduces the per-GPU device times.
+struct JobPass { double box_ms = 0, decode_ms = 0, synth_ms = 0; unsigned long long errors = 0, worst = 0, bits = 0, launches = 0; bool ok = true; std::string err; };
+
+static JobPass runJobPass(const Args& a, int gatherMode, std::vector<vit_comm*>& comms) {
+    JobPass pass;
+    std::vector<vit_job_result> res(a.gpus);
+    std::vector<std::string> errs(a.gpus);
+    std::vector<std::thread> workers;
+    const unsigned seed = a.seed < 0 ? 1u : static_cast<unsigned>(a.seed);
+    for (int g = 0; g < a.gpus; ++g)
+        workers.emplace_back([&, g] {
+            vit_job_config cfg{};
+            cfg.options = a.options; cfg.n_bits = a.messageLen; cfg.nstreams = static_cast<unsigned>(a.streams);
+            cfg.wave = static_cast<unsigned>(a.wave); cfg.batch = static_cast<unsigned>(a.batch); cfg.seed = seed;
+            cfg.source = a.prbs ? 1 : 0; cfg.amp = 0; cfg.sigma = std::pow(10.0, -a.snr / 5.0); cfg.gather = gatherMode; cfg.root = 0;
+            vit_job* job = nullptr;
+            int rc = vit_job_create(&job, a.gpus > 1 ? comms[g] : nullptr, g, &cfg);
+            if (rc == VIT_OK) rc = vit_job_run(job, &res[g]);
+            if (rc != VIT_OK) errs[g] = vit_last_error();
+            vit_job_destroy(job);
+        });
+    for (auto& w : workers) w.join();
+    for (int g = 0; g < a.gpus; ++g) {
+        if (!errs[g].empty()) { pass.ok = false; pass.err = "GPU " + std::to_string(g) + ": " + errs[g]; return pass; }
+        pass.box_ms = std::max(pass.box_ms, res[g].job_ms);
+        pass.decode_ms = std::max(pass.decode_ms, res[g].decode_ms);
+        pass.synth_ms = std::max(pass.synth_ms, res[g].synth_ms);
+        pass.errors += res[g].bit_errors; pass.worst = std::max(pass.worst, res[g].max_stream_errors);
+        pass.bits += res[g].decoded_bits; pass.launches += res[g].launches;
+    }
+    return pass;
+}
+
+static int runStreamJob(const Args& a) {
+    if (!vit_options_valid(a.options)) { std::cerr << "Error: unsupported option combination." << std::endl; return -1; }
+    if (vit_dev_count() < a.gpus) { std::cerr << "Error: " << a.gpus << " GPUs requested, " << vit_dev_count() << " present." << std::endl; return -1; }
+    const int mode = a.gather == "nccl" ? VIT_GATHER_NCCL : a.gather == "copy" ? VIT_GATHER_COPY : a.gather == "direct" ? VIT_GATHER_DIRECT : VIT_GATHER_NONE;
+    std::vector<vit_comm*> comms(a.gpus, nullptr);
+    if (a.gpus > 1) VIT_HANDLE_ERROR(vit_comm_init_all(comms.data(), a.gpus, nullptr));
+    std::cout << "Stream job: " << a.streams << " streams x " << a.messageLen << " bits, options 0x" << std::hex << a.options << std::dec
+              << ", " << a.gpus << " GPU(s), wave " << a.wave << ", batch " << a.batch << ", gather " << a.gather
+              << (a.gpus > 1 ? ", NCCL " + std::to_string(vit_comm_nccl_version()) : std::string()) << std::endl;
+    int rc = 0;
+    for (int which = 0; which < (mode == VIT_GATHER_NONE ? 1 : 2); ++which) {
+        const int m = which == 0 ? mode : VIT_GATHER_NONE;
+        const JobPass p = runJobPass(a, m, comms);
+        if (!p.ok) { std::cerr << "Error: " << p.err << std::endl; rc = -1; break; }
+        std::cout << (m == VIT_GATHER_NONE ? "without gather" : "with gather (" + a.gather + ")") << " -> box time: " << p.box_ms
+                  << " ms (decode " << p.decode_ms << " ms, max over GPUs; generation " << p.synth_ms << " ms not counted)   decoded: "
+                  << p.bits << " bits   " << p.bits / (p.box_ms * 1e6) << " Gb/s   launches: " << p.launches << "   BEN: " << p.errors
+                  << "   BER: " << static_cast<double>(p.errors) / static_cast<double>(p.bits) << "   worst stream BEN: " << p.worst << std::endl;
+    }
+    for (auto* c : comms) vit_comm_destroy(c);
+    return rc;
+}
+
 // runtime options -> template instantiation (the reference: 60 nested-macro cases, main.cpp:79-104)
 template <int options>
 bool tryRun(const Args& a, Outcome& out) {
@@ -223,6 +279,7 @@ int main(int argc, char* argv[]) {
                   << "Output Type: " << ((a.options & DECODE_MASK) == O_B16 ? "16-bit" : "32-bit") << "\n"
                   << "Computation Mode: " << ((a.options & COMP_MASK) == REG ? "Regular" : "DPX") << "\n" << std::endl;
     }
+    if (a.streams > 1 || a.gpus > 1) return runStreamJob(a);
     Outcome out;
     if (!dispatch(a, out, std::make_integer_sequence<int, 60>{})) {
         std::cerr << "Error: unsupported option combination." << std::endl;
@@ -232,7 +289,6 @@ int main(int argc, char* argv[]) {
     std::cout << "Final results -> BEN: " << out.ben << "   BER: " << static_cast<double>(out.ben) / a.messageLen << std::endl;  // main.cpp:107-110
     std::cout << "Decoder -> kernel time: " << out.best_ms << " ms   decoded: " << out.decoded << " bits   "
               << out.decoded / (out.best_ms * 1e6) << " Gb/s";
-    if (out.box_gbps > 0) std::cout << "   box (" << a.streams << " streams / " << a.gpus << " GPUs): " << out.box_gbps << " Gb/s";
     std::cout << std::endl;
     return 0;
 }

@@ -35,7 +35,8 @@ enum {
     VIT_OK = 0,
     VIT_ERR_OPTIONS = 1,   /* option combination not supported */
     VIT_ERR_CUDA = 2,      /* a CUDA runtime call failed */
-    VIT_ERR_ARG = 3        /* bad pointer / alignment / size */
+    VIT_ERR_ARG = 3,       /* bad pointer / alignment / size */
+    VIT_ERR_NCCL = 4       /* an NCCL call failed, or libnccl.so.2 could not be loaded */
 };
 
 /* replaces ViterbiCUDA<options>::ViterbiCUDA() and ViterbiCUDA(size_t inputNum)
@@ -57,7 +58,7 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
  *   AUTO        time-sliced upload (one decode launch that waits, inside the kernel, for column blocks of its input)
  *               when copies can run beside kernels, otherwise as CHUNKED.  Pinned buffers are read/written in place;
  *               pageable buffers (the reference's calling convention, viterbiDF.h:188-193) are staged through pinned
- *               buffers by worker threads (VIT_STAGE_THREADS, default min(8, cores/2)).  A run with kernel_ms != NULL
+ *               buffers by worker threads (VIT_STAGE_THREADS, default min(16, cores); the caller is blocked meanwhile).  A run with kernel_ms != NULL
  *               always takes the SEQUENTIAL path, so that the reported time is the decode kernel alone.
  *   SEQUENTIAL  the reference's copy -> launch -> copy sequence (viterbi.cu:219-235).
  *   CHUNKED     segment-range pipeline: pinned buffers only, pageable buffers fall back to SEQUENTIAL.
@@ -134,11 +135,92 @@ int vit_count_errors_device(int options, const void* out_d, const void* bits_d, 
 int vit_dev_alloc(void** ptr, size_t bytes);
 void vit_dev_free(void* ptr);
 int vit_dev_sync(void);
+int vit_dev_set(int device);                 /* cudaSetDevice for the calling thread */
+int vit_dev_copy_to_host(void* dst_h, const void* src_d, size_t bytes);      /* synchronous */
+int vit_dev_copy_from_host(void* dst_d, const void* src_h, size_t bytes);
 int vit_dev_count(void);
 /* page-locked (pinned) host memory: vit_run reads and writes such buffers in place (no staging copy); pageable buffers are
  * staged through the handle's own pinned buffers by worker threads (see vit_set_upload_mode) */
 int vit_host_alloc(void** ptr, size_t bytes);
 void vit_host_free(void* ptr);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (new; the reference is single-GPU, cudaSetDevice(0) at src/viterbi/viterbi.cu:134).  Independent codeword
+ * streams are sharded over the GPUs of one box -- one decoder per GPU, a stream is never split -- and only the packed
+ * output bits cross GPUs: they are gathered into one stream-major buffer on a root GPU (BASELINE.json
+ * configs[4]).  NCCL is loaded at run time (dlopen of libnccl.so.2), the library has no link dependency on it.
+ * A communicator is either one of N created by ONE process for N GPUs (vit_comm_init_all; one host thread per GPU then
+ * drives its own communicator) or this process's rank in a job of N processes (vit_comm_init_rank; the 128-byte id comes
+ * from vit_comm_get_unique_id on one rank and is distributed by the caller, e.g. over torch.distributed or MPI).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct vit_comm vit_comm;
+#define VIT_COMM_ID_BYTES 128
+int vit_comm_available(void);                 /* 1 if libnccl.so.2 could be loaded */
+int vit_comm_nccl_version(void);              /* e.g. 22809, 0 if unavailable */
+int vit_comm_get_unique_id(void* id128);
+int vit_comm_init_rank(vit_comm** out, int nranks, int rank, const void* id128, int device);
+int vit_comm_init_all(vit_comm** out /* [ndev] */, int ndev, const int* devices /* NULL: 0..ndev-1 */);
+void vit_comm_destroy(vit_comm* c);
+int vit_comm_rank(const vit_comm* c);
+int vit_comm_size(const vit_comm* c);
+/* host-side: wait for this rank's gathers, then meet the other ranks; afterwards the root's buffer is complete */
+int vit_comm_barrier(vit_comm* c);
+/* make a stream wait for the gathers this rank has issued so far */
+int vit_comm_stream_wait(vit_comm* c, void* cuda_stream);
+/* the stream the gathers run on (a cudaStream_t) */
+void* vit_comm_stream(vit_comm* c);
+
+/* contiguous block partition of nstreams over nranks: rank r owns [first, first + count); blocks differ by <= 1 */
+void vit_shard_range(size_t nstreams, int nranks, int rank, size_t* first, size_t* count);
+int vit_shard_owner(size_t nstreams, int nranks, size_t stream);
+
+/* how packed output bits reach the root */
+enum {
+    VIT_GATHER_NONE = 0,    /* they stay on the decoding GPU */
+    VIT_GATHER_NCCL = 1,    /* grouped ncclSend/ncclRecv to the root on a side stream, overlapping the next decode */
+    VIT_GATHER_COPY = 2,    /* device-to-device copy into the root's buffer (copy engines over NVLink, no SMs) */
+    VIT_GATHER_DIRECT = 3   /* the decode kernel stores straight into the root's buffer over NVLink (no gather step) */
+};
+/* collective: a device buffer on the root's GPU addressable by every rank (root: the allocation, others: a mapping
+ * through CUDA IPC / peer access).  Owned by the communicator. */
+int vit_comm_shared_alloc(vit_comm* c, void** ptr, size_t bytes, int root);
+/* rank p's block (sizes[p] bytes at send_d on rank p) lands at recv_base + offsets[p] on the root; every rank passes the
+ * same offsets/sizes (one entry per rank).  Ordered after the work queued on producer_stream; asynchronous. */
+int vit_comm_gatherv(vit_comm* c, int mode, const void* send_d, void* recv_base, const size_t* offsets,
+                     const size_t* sizes, int root, void* producer_stream);
+
+/* The sharded stream job: `nstreams` independent streams of n_bits message bits each (stream s: synthetic source with
+ * seed + s), dealt to the ranks in contiguous blocks; per round every rank generates `batch` of its streams on the device
+ * (untimed), decodes them `wave` streams per launch and gathers each finished wave while the next one decodes. */
+typedef struct {
+    int options;            /* option bitfield */
+    size_t n_bits;          /* message bits per stream */
+    unsigned nstreams;      /* streams of the whole job, all ranks together */
+    unsigned wave;          /* streams per decode launch */
+    unsigned batch;         /* streams generated ahead of each timed decode phase (device memory: batch x (in + out)) */
+    unsigned seed;
+    int source;             /* 0: counter hash, 1: PRBS-31 */
+    int amp;                /* symbol amplitude in quantiser units, <= 0: default per input type */
+    double sigma;           /* noise sd relative to amp */
+    int gather;             /* VIT_GATHER_* */
+    int root;
+} vit_job_config;
+typedef struct {
+    double decode_ms;       /* this rank: device time of the decode launches, summed over the rounds */
+    double job_ms;          /* this rank: ... up to the end of the round's last gather (== decode_ms without gather) */
+    double synth_ms;        /* generation, not part of the job time */
+    unsigned long long decoded_bits, bit_errors, max_stream_errors, launches;
+    unsigned streams;       /* streams this rank decoded */
+} vit_job_result;
+typedef struct vit_job vit_job;
+int vit_job_create(vit_job** out, vit_comm* comm /* NULL: one GPU */, int device, const vit_job_config* cfg);
+int vit_job_run(vit_job* job, vit_job_result* result);
+/* root: the stream-major gathered outputs (stream s at + s * out_stride), a device pointer; NULL with VIT_GATHER_NONE */
+const void* vit_job_gathered(const vit_job* job, size_t* out_stride);
+int vit_job_stream_range(const vit_job* job, size_t* first, size_t* count);
+/* bit errors of each of this rank's streams in the last run */
+int vit_job_stream_errors(const vit_job* job, unsigned long long* errs, size_t cap);
+void vit_job_destroy(vit_job* job);
 
 const char* vit_last_error(void);
 

@@ -117,7 +117,7 @@ def test_config4_fp32_4G_single_stream(V, O):
     assert M == 3_999_999_936
     d_in = torch.empty(dec.getInputSize(N) + 256, dtype=torch.uint8, device="cuda")
     d_out = torch.zeros(out_b + 256, dtype=torch.uint8, device="cuda")
-    for seed, sigma in ((11, 0.25), (12, 0.9)):
+    for seed, sigma in ((11, 0.25), (12, 0.7)):
         V.synth_device(4, n_bits, d_in.data_ptr(), None, seed=seed, sigma=sigma)
         ms = dec.run_device(d_in.data_ptr(), d_out.data_ptr(), N, want_kernel_time=True)
         errs = V.count_errors_synth_device(opt, d_out.data_ptr(), M, seed=seed)
@@ -125,7 +125,7 @@ def test_config4_fp32_4G_single_stream(V, O):
         if sigma < 0.5:
             assert errs == 0
         else:
-            assert 0 < errs < M // 100
+            assert 0 < errs < M // 4
         for a, b in ((0, 3), (3199, 3202), (6397, 6400)):
             b0, nb, w0, nw = O.segment_window(opt, N, a, b)
             w0, exp = O.decode_window(opt, d_in[b0:b0 + nb].cpu().numpy(), N, a, b)

@@ -50,7 +50,7 @@ def test_host_run_pinned_pageable_mixes(V, O, opt, n, pin_in, pin_out):
 
 def test_upload_modes_give_identical_output(V, O):
     import torch
-    opt, n = 0x011, 6400 * 32 * 40 + 32 * 17 + 64
+    opt, n = 0x011, 6400 * 32 * 55 + 32 * 17 + 64          # 11.3 MB of input: two chunks of the segment-range pipeline
     bits, packed, N = O.make_channel_det(n, opt & 0xF, seed=79, sigma=0.8)
     exp = O.decode(opt, packed, N)
     dec = V.ViterbiCUDA(opt, N)

@@ -1,6 +1,7 @@
-"""CPU test of the N>1 path: world_size-2 gloo run of the stream sharding + output gather.  The per-rank
-decode is stood in for by the golden model (test infrastructure); the partition and gather code is the
-product's (gpu-accelerated-viterbi-decoder_b200/sharding.py), the same code bench.py runs over NCCL."""
+"""CPU test of the N>1 path: world_size-2 gloo run of the stream sharding + gather-to-root protocol.  The per-rank
+decode is stood in for by the golden model (test infrastructure) and gloo send/recv stands in for NCCL send/recv; the
+partition (C ABI vit_shard_range / vit_shard_owner, csrc/vit_mg.cu) and the per-wave offsets/sizes every rank derives
+from it (sharding.wave_blocks == what vit_job_run passes to vit_comm_gatherv) are the product's."""
 import os
 import subprocess
 import sys
@@ -8,7 +9,7 @@ import textwrap
 
 import pytest
 
-from vit_testlib import ROOT
+from vit_testlib import ROOT, load_pkg
 
 WORKER = textwrap.dedent('''
     import os, sys
@@ -16,36 +17,60 @@ WORKER = textwrap.dedent('''
     sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
     from vit_testlib import load_pkg
     from oracle import oracle as O
+    V = load_pkg()
     import importlib.util
     spec = importlib.util.spec_from_file_location("vit_sharding", os.path.join(%(root)r, "gpu-accelerated-viterbi-decoder_b200", "sharding.py"))
     S = importlib.util.module_from_spec(spec); spec.loader.exec_module(S)
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    n_streams, n_bits, opt = 5, 64 + 16 * 900, 0x112
+    n_streams, n_bits, opt, batch, wave, root = 7, 64 + 16 * 900, 0x112, 2, 2, 0
+    out_bytes = O.output_size(opt, 2 * n_bits)
+    out_stride = (out_bytes + 255) // 256 * 256
     mine = S.streams_of_rank(n_streams, world, rank)
-    outs = []
-    for s in mine:
-        bits, packed, N = O.make_channel_det(n_bits, O.SOFT8, seed=100 + s, sigma=0.9)
-        outs.append(torch.from_numpy(O.decode(opt, packed, N).astype(np.int32)))
-    local = torch.stack(outs) if outs else torch.zeros((0, O.output_size(opt, 2 * n_bits) // 2), dtype=torch.int32)
-    full = S.gather_packed_outputs(dist, local, n_streams, world, rank)
-    assert full.shape[0] == n_streams
-    for s in range(n_streams):
-        bits, packed, N = O.make_channel_det(n_bits, O.SOFT8, seed=100 + s, sigma=0.9)
-        assert np.array_equal(full[s].numpy().astype(np.uint16), O.decode(opt, packed, N)), (rank, s)
-        assert S.owner_of_stream(n_streams, world, s) == [k for k in range(world) if s in S.streams_of_rank(n_streams, world, k)][0]
+    gathered = torch.zeros(n_streams * out_stride, dtype=torch.uint8) if rank == root else None
+    max_count = len(S.streams_of_rank(n_streams, world, 0))
+    for rnd in range((max_count + batch - 1) // batch):
+        for w0 in range(0, batch, wave):
+            offsets, sizes = S.wave_blocks(n_streams, world, batch, wave, out_stride, rnd, w0)
+            # this rank's block of the wave: decode its streams (golden model stands in for the GPU)
+            block = torch.zeros(sizes[rank], dtype=torch.uint8)
+            for k in range(sizes[rank] // out_stride):
+                s = offsets[rank] // out_stride + k
+                assert s in mine
+                bits, packed, N = O.make_channel_det(n_bits, O.SOFT8, seed=100 + s, sigma=0.9)
+                block[k * out_stride:k * out_stride + out_bytes] = torch.from_numpy(O.decode(opt, packed, N).view(np.uint8).copy())
+            if rank == root:
+                gathered[offsets[root]:offsets[root] + sizes[root]] = block
+                for p in range(world):
+                    if p != root and sizes[p]:
+                        buf = torch.zeros(sizes[p], dtype=torch.uint8)
+                        dist.recv(buf, src=p)
+                        gathered[offsets[p]:offsets[p] + sizes[p]] = buf
+            elif sizes[rank]:
+                dist.send(block, dst=root)
     dist.barrier()
-    if rank == 0:
+    if rank == root:
+        for s in range(n_streams):
+            bits, packed, N = O.make_channel_det(n_bits, O.SOFT8, seed=100 + s, sigma=0.9)
+            got = gathered[s * out_stride:s * out_stride + out_bytes].numpy().view(np.uint16)
+            assert np.array_equal(got, O.decode(opt, packed, N)), s
+            assert S.owner_of_stream(n_streams, world, s) == [k for k in range(world) if s in S.streams_of_rank(n_streams, world, k)][0]
         print("SHARDING_OK")
     dist.destroy_process_group()
 ''')
 
 
-def test_partition_is_a_partition():
+def _sharding():
     import importlib.util
+    load_pkg()
     spec = importlib.util.spec_from_file_location("vit_sharding", os.path.join(ROOT, "gpu-accelerated-viterbi-decoder_b200", "sharding.py"))
     S = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(S)
+    return S
+
+
+def test_partition_is_a_partition():
+    S = _sharding()
     for n in (0, 1, 7, 8, 1024, 1025):
         for world in (1, 2, 3, 4, 8):
             seen = []
@@ -56,6 +81,24 @@ def test_partition_is_a_partition():
             assert max(sizes) - min(sizes) <= 1
             for s in range(n):
                 assert s in S.streams_of_rank(n, world, S.owner_of_stream(n, world, s))
+
+
+def test_wave_blocks_tile_the_gathered_buffer():
+    """Over all rounds and waves the per-rank blocks cover every stream exactly once, in stream-major order."""
+    S = _sharding()
+    for n, world, batch, wave in ((1024, 8, 32, 16), (7, 2, 2, 2), (5, 4, 4, 2), (9, 3, 2, 1)):
+        stride = 256
+        covered = []
+        max_count = len(S.streams_of_rank(n, world, 0))
+        for rnd in range((max_count + batch - 1) // batch):
+            for w0 in range(0, batch, wave):
+                offsets, sizes = S.wave_blocks(n, world, batch, wave, stride, rnd, w0)
+                for p in range(world):
+                    for k in range(sizes[p] // stride):
+                        s = offsets[p] // stride + k
+                        assert S.owner_of_stream(n, world, s) == p
+                        covered.append(s)
+        assert sorted(covered) == list(range(n)), (n, world, batch, wave)
 
 
 def test_two_rank_gloo_gather(tmp_path):
