@@ -19,6 +19,7 @@ HARD, SOFT4, SOFT8, SOFT16, FP32 = 0x0, 0x1, 0x2, 0x3, 0x4
 M_B32, M_B16, M_FP16 = 0x00, 0x10, 0x20
 O_B32, O_B16 = 0x000, 0x100
 REG, DPX = 0x0000, 0x1000
+DPX_TIES = 0x2000   # extension (not a reference value): int32 core with the tie rule of the reference's dead DPX code paths
 CHANNEL_MASK, METRIC_MASK, DECODE_MASK, COMP_MASK = 0xF, 0xF0, 0xF00, 0xF000
 
 # window constants, reference viterbi.h:61-79
@@ -141,7 +142,7 @@ def parse_options(input="h", metric="b32", output="b32", comp="reg"):
          "SOFT16": SOFT16, "s16": SOFT16, "FP32": FP32, "f": FP32}[input]
     m = {"b16": M_B16, "b32": M_B32, "f16": M_FP16}[metric]
     o = {"b16": O_B16, "b32": O_B32}[output]
-    c = {"REG": REG, "reg": REG, "DPX": DPX, "dpx": DPX}[comp]
+    c = {"REG": REG, "reg": REG, "DPX": DPX, "dpx": DPX, "DPXT": DPX_TIES, "dpxt": DPX_TIES}[comp]
     return i | m | o | c
 
 

@@ -183,12 +183,17 @@ inline int met_type(int o) { return (o >> 4) & 0xf; }
 inline int out_type(int o) { return (o >> 8) & 0xf; }
 inline int bpp_of(int o) { return out_type(o) == 1 ? 16 : 32; }
 
+inline int comp_mode(int o) { return (o >> 12) & 0xf; }
+
+// CompMode: 0 REG, 1 DPX (the reference's flag; selects the same core as REG there and here), 2 DPX_TIES (extension: the
+// tie rule the reference's DPX code would have if it were instantiated -- differs from REG for the int32 core only)
 bool fields_known(int o) {
-    return in_type(o) <= 4 && met_type(o) <= 2 && out_type(o) <= 1 && ((o >> 12) & 0xf) <= 1 && (o >> 16) == 0;
+    return in_type(o) <= 4 && met_type(o) <= 2 && out_type(o) <= 1 && comp_mode(o) <= 2 && (o >> 16) == 0;
 }
 
 const vitk::KernelEntry* entry_for(int o) {
-    int met = met_type(o) == 0 ? vitk::MET_B32 : met_type(o) == 1 ? vitk::MET_B16 : vitk::MET_F16;
+    int met = met_type(o) == 0 ? (comp_mode(o) == 2 ? vitk::MET_B32D : vitk::MET_B32) : met_type(o) == 1 ? vitk::MET_B16 : vitk::MET_F16;
+    if (comp_mode(o) == 2 && met_type(o) == 2) return nullptr;      // the reference has no half2 DPX code (viterbi.h:30-31)
     return vitk::kernel_entry(met, in_type(o), out_type(o));
 }
 
@@ -198,6 +203,7 @@ namespace vitk {
 const KernelEntry* kernel_entry(int met, int in, int bpp16) {
     switch (met) {
         case MET_B32: return kernel_entry_b32(in, bpp16);
+        case MET_B32D: return kernel_entry_b32d(in, bpp16);
         case MET_B16: return kernel_entry_b16(in, bpp16);
         case MET_F16: return kernel_entry_f16(in, bpp16);
         default: return nullptr;
@@ -581,6 +587,7 @@ size_t vit_output_size(int o, size_t n) { return vit_message_len(o, n) / 8; }
 int vit_options_valid_ref(int o) {
     if (!fields_known(o)) return 0;
     const int it = in_type(o), mt = met_type(o), cm = (o >> 12) & 0xf;
+    if (cm > 1) return 0;
     if (it == 2 && mt == 2) return 0;
     if (it == 3 && mt == 2) return 0;
     if (it == 3 && mt == 1) return 0;

@@ -53,7 +53,11 @@
 namespace vitk {
 
 enum { IN_HARD = 0, IN_S4 = 1, IN_S8 = 2, IN_S16 = 3, IN_F32 = 4 };
-enum { MET_B32 = 0, MET_B16 = 1, MET_F16 = 2 };
+enum { MET_B32 = 0, MET_B16 = 1, MET_F16 = 2,
+       // int32 core with the tie rule of the reference's never-instantiated DPX variant (viterbiACS.cuh:123-134: the partner
+       // wins ties in every phase; the REG variant lets the odd predecessor win at phase 0).  Same instructions as MET_B32.
+       MET_B32D = 3 };
+constexpr bool is_b32(int met) { return met == MET_B32 || met == MET_B32D; }
 
 struct KParams {
     const uint8_t* in;              // stream 0 channel words
@@ -417,6 +421,7 @@ template <int IN> struct Core<MET_B32, IN> {
     static VIT_HD uint32_t enc(int v) { return (uint32_t)v; }
     static VIT_HD uint32_t zero() { return 0; }
 };
+template <int IN> struct Core<MET_B32D, IN> : Core<MET_B32, IN> {};
 
 // candidate of `metric` along the branch whose operand type is `type` (see bm_type), given the
 // table entry (w0 = X word, w1 = Y word); `opposite` = the other branch into the same state

@@ -15,6 +15,7 @@ const KernelEntry* kernel_entry(int met, int in, int bpp16);
 
 // defined by the instantiation units
 const KernelEntry* kernel_entry_b32(int in, int bpp16);
+const KernelEntry* kernel_entry_b32d(int in, int bpp16);
 const KernelEntry* kernel_entry_b16(int in, int bpp16);
 const KernelEntry* kernel_entry_f16(int in, int bpp16);
 }  // namespace vitk

@@ -42,7 +42,8 @@ static void usage(const char* prog) {
               << "  -i, --input <type>       Set the input channel type (HARD|h, SOFT4|s4, SOFT8|s8, SOFT16|s16, FP32|f).\n"
               << "  -m, --metric <type>      Set the metric type (b16, b32, f16).\n"
               << "  -o, --output <type>      Set the output type (b16, b32).\n"
-              << "  -c, --compMode <type>    Set the computation mode (REG|reg, DPX|dpx).\n"
+              << "  -c, --compMode <type>    Set the computation mode (REG|reg, DPX|dpx; as in the reference both run the\n"
+              << "                           same core.  DPXT|dpxt: the tie rule of the reference's dormant DPX code).\n"
               << "  -v, --verbose            Enable verbose output.\n"
               << "      --seed <integer>     Fixed seed for bits (noise uses seed+1); default: random_device.\n"
               << "      --prbs               PRBS-31 message bits instead of mt19937.\n"
@@ -90,7 +91,7 @@ static Args parseArg(int argc, char* argv[]) {
         else if (f == "-o" || f == "--output")
             a.options = (a.options & ~DECODE_MASK) | lookup(f, value(), {{"b16", O_B16}, {"b32", O_B32}});
         else if (f == "-c" || f == "--compMode")
-            a.options = (a.options & ~COMP_MASK) | lookup(f, value(), {{"REG", REG}, {"reg", REG}, {"DPX", DPX}, {"dpx", DPX}});
+            a.options = (a.options & ~COMP_MASK) | lookup(f, value(), {{"REG", REG}, {"reg", REG}, {"DPX", DPX}, {"dpx", DPX}, {"DPXT", DPX_TIES}, {"dpxt", DPX_TIES}});
         else if (f == "-v" || f == "--verbose") a.verbose = true;
         else if (f == "--prbs") a.prbs = true;
         else if (f == "--device-source") a.deviceSource = true;
@@ -261,7 +262,7 @@ template <int... I>
 bool dispatch(const Args& a, Outcome& out, std::integer_sequence<int, I...>) {
     // index = in + 5*(met + 3*(out + 2*cmp))
     return (tryRun<((I % 5) << CHANNEL_SHIFT) | (((I / 5) % 3) << METRIC_SHIFT) | (((I / 15) % 2) << DECODE_SHIFT) |
-                   ((I / 30) << COMP_SHIFT)>(a, out) || ...);
+                   ((I / 30) << COMP_SHIFT)>(a, out) || ...);      // I / 30: REG, DPX, DPX_TIES
 }
 
 int main(int argc, char* argv[]) {
@@ -277,11 +278,11 @@ int main(int argc, char* argv[]) {
                   << "Input Channel Type: " << inNames[in >> CHANNEL_SHIFT] << "\n"
                   << "Metric Type: " << (met == M_B16 ? "16-bit" : met == M_B32 ? "32-bit" : "FP16") << "\n"
                   << "Output Type: " << ((a.options & DECODE_MASK) == O_B16 ? "16-bit" : "32-bit") << "\n"
-                  << "Computation Mode: " << ((a.options & COMP_MASK) == REG ? "Regular" : "DPX") << "\n" << std::endl;
+                  << "Computation Mode: " << ((a.options & COMP_MASK) == REG ? "Regular" : (a.options & COMP_MASK) == DPX ? "DPX" : "DPX tie rule") << "\n" << std::endl;
     }
     if (a.streams > 1 || a.gpus > 1) return runStreamJob(a);
     Outcome out;
-    if (!dispatch(a, out, std::make_integer_sequence<int, 60>{})) {
+    if (!dispatch(a, out, std::make_integer_sequence<int, 90>{})) {
         std::cerr << "Error: unsupported option combination." << std::endl;
         return -1;
     }

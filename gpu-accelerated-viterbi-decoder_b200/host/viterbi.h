@@ -26,7 +26,10 @@ enum ChannelIn { HARD = 0 << CHANNEL_SHIFT, SOFT4 = 1 << CHANNEL_SHIFT, SOFT8 = 
                  SOFT16 = 3 << CHANNEL_SHIFT, FP32 = 4 << CHANNEL_SHIFT };
 enum Metric { M_B32 = 0 << METRIC_SHIFT, M_B16 = 1 << METRIC_SHIFT, M_FP16 = 2 << METRIC_SHIFT };
 enum DecodeOut { O_B32 = 0 << DECODE_SHIFT, O_B16 = 1 << DECODE_SHIFT };
-enum CompMode { REG = 0 << COMP_SHIFT, DPX = 1 << COMP_SHIFT };
+enum CompMode { REG = 0 << COMP_SHIFT, DPX = 1 << COMP_SHIFT,
+                // extension (not a reference value): the tie rule the reference's DPX code paths define but never run
+                // (viterbiACS.cuh:123-134; viterbi.cu:181,192,204 do not forward compMode) -- int32 core only differs
+                DPX_TIES = 2 << COMP_SHIFT };
 
 // Which combinations exist.  The reference (viterbi.h:22-36) excludes f16 x {s8,s16}, b16 x s16 and
 // f16 x dpx; this library adds f16 x {s8,s16} (symbols pre-scaled to 5 bits) and treats dpx as an
@@ -35,11 +38,11 @@ template <int options>
 struct OptionsValid {
     static constexpr int in = options & CHANNEL_MASK, met = options & METRIC_MASK,
                          out = options & DECODE_MASK, cmp = options & COMP_MASK;
-    static constexpr bool known = in <= FP32 && met <= M_FP16 && out <= O_B16 && cmp <= DPX && (options >> 16) == 0;
-    static constexpr bool value = known && !(met == M_B16 && in == SOFT16);
+    static constexpr bool known = in <= FP32 && met <= M_FP16 && out <= O_B16 && cmp <= DPX_TIES && (options >> 16) == 0;
+    static constexpr bool value = known && !(met == M_B16 && in == SOFT16) && !(met == M_FP16 && cmp == DPX_TIES);
     // the reference's own table, for callers that want to stay inside it
     static constexpr bool reference_value =
-        known && !((in == SOFT8 || in == SOFT16) && met == M_FP16) && !(in == SOFT16 && met == M_B16) &&
+        known && cmp <= DPX && !((in == SOFT8 || in == SOFT16) && met == M_FP16) && !(in == SOFT16 && met == M_B16) &&
         !(met == M_FP16 && cmp == DPX);
 };
 

@@ -11,7 +11,11 @@
  *   bits 4-7  Metric    : B32=0x00 B16=0x10 FP16=0x20
  *   bits 8-11 DecodeOut : O_B32=0x000 O_B16=0x100
  *   bits 12-15 CompMode : REG=0x0000 DPX=0x1000 (both select the same core, as in the reference
- *                         where the flag is never forwarded: viterbi.cu:181,192,204)
+ *                         where the flag is never forwarded: viterbi.cu:181,192,204);
+ *                         extension DPX_TIES=0x2000: the tie rule the reference's DPX code paths define
+ *                         (viterbiACS.cuh:101-110,123-134,205-213,224-236) but never run -- identical to REG for
+ *                         the int16x2 core, "the partner wins ties in every phase" for the int32 core, rejected
+ *                         for the half2 core (the reference has no half2 DPX code)
  * Every size argument called `inputNum` is the number of CODED SYMBOLS (2 x message bits), exactly
  * as in the reference (viterbi.cu:63-92,210-215).
  *

@@ -16,6 +16,7 @@ HARD, SOFT4, SOFT8, SOFT16, FP32 = 0, 1, 2, 3, 4
 M_B32, M_B16, M_FP16 = 0x00, 0x10, 0x20
 O_B32, O_B16 = 0x000, 0x100
 REG, DPX = 0x0000, 0x1000
+DPX_TIES = 0x2000   # extension: the tie rule of the reference's (never instantiated) DPX code paths, see vit_oracle.h
 FLAG_REF_OVERRUN = 1
 SEGMENTS = 6400
 EXTRA_L = 26
@@ -260,6 +261,36 @@ def ref_lib():
         L.ref_device_count.restype = C.c_int
         _ref = L
     return _ref
+
+
+_ref_dpx = None
+
+
+def ref_dpx_lib():
+    """oracle/_ref/libvitref_dpx.so (the reference sources with compMode forwarded to forwardACS, ref_dpx_shim.cu) or None."""
+    global _ref_dpx
+    if _ref_dpx is None:
+        so = os.path.join(_HERE, "_ref", "libvitref_dpx.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_run_dpx.restype = C.c_int
+        L.ref_run_dpx.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_float)]
+        _ref_dpx = L
+    return _ref_dpx
+
+
+def ref_decode_dpx(options, packed, input_num):
+    """Run the reference decoder with its DPX code paths live (GPU).  options: the reference's own bitfield with
+    CompMode DPX (0x1000).  Returns (out, kernel_ms)."""
+    packed = np.ascontiguousarray(packed)
+    nwords = output_size(options, input_num) // np.dtype(out_dtype(options)).itemsize
+    out = np.zeros(nwords + 8, out_dtype(options))
+    ms = C.c_float(0)
+    rc = ref_dpx_lib().ref_run_dpx(options, _ptr(packed), _ptr(out), input_num, C.byref(ms))
+    if rc != 0:
+        raise ValueError("reference rejects option combination 0x%x" % options)
+    return out[:nwords], ms.value
 
 
 def ref_sizes(options, n):

@@ -49,6 +49,7 @@ int sizes_one(size_t inputNum, size_t* v) {
 }  // namespace
 
 extern "C" {
+#pragma GCC visibility push(default)
 
 int ref_run(int options, const void* in_h, void* out_h, size_t inputNum, float* kernel_ms) {
 #define FN run_one
@@ -72,4 +73,5 @@ int ref_device_count(void) {
     return n;
 }
 
+#pragma GCC visibility pop
 }  // extern "C"

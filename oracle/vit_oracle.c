@@ -41,6 +41,7 @@ int vo_num_threads(void) {
 /* viterbi.h:22-36 */
 int vo_options_valid_ref(int o) {
     int it = in_type(o), mt = metric_type(o), cm = o & 0xf000;
+    if (cm > VO_DPX) return 0;
     if (it == VO_SOFT8 && mt == VO_M_FP16) return 0;
     if (it == VO_SOFT16 && mt == VO_M_FP16) return 0;
     if (it == VO_SOFT16 && mt == VO_M_B16) return 0;
@@ -226,6 +227,7 @@ static void decode_segment(const dec_ctx* c, size_t w) {
         int tie_u0, tie_u1;
         if (mt == VO_M_FP16) { tie_u0 = 0; tie_u1 = 1; }
         else if (mt == VO_M_B16) { tie_u0 = 1; tie_u1 = 0; }
+        else if ((o & 0xf000) == VO_DPX_TIES) { tie_u0 = 1; tie_u1 = 0; }   /* viterbiACS.cuh:123-134,224-236 (DPX variants) */
         else { tie_u0 = 1; tie_u1 = (phase == 0) ? 1 : 0; }
 
         for (int j = 0; j < 32; j++) {
@@ -282,6 +284,8 @@ static int decode_range(int options, const void* in, size_t in_off, size_t in_av
     if (it > VO_FP32) return -1;
     if (mt != VO_M_B32 && mt != VO_M_B16 && mt != VO_M_FP16) return -1;
     if (mt == VO_M_B16 && it == VO_SOFT16) return -1;                  /* viterbi.h:28-29 */
+    if ((options & 0xf000) == VO_DPX_TIES && mt == VO_M_FP16) return -1; /* no half2 DPX code in the reference */
+    if ((options & 0xf000) > VO_DPX_TIES) return -1;
     dec_ctx c;
     c.options = options; c.flags = flags;
     c.in = (const uint8_t*)in; c.in_bytes = vo_input_size(options, inputNum);

@@ -28,7 +28,13 @@ enum {
     VO_HARD = 0x0, VO_SOFT4 = 0x1, VO_SOFT8 = 0x2, VO_SOFT16 = 0x3, VO_FP32 = 0x4,
     VO_M_B32 = 0x00, VO_M_B16 = 0x10, VO_M_FP16 = 0x20,
     VO_O_B32 = 0x000, VO_O_B16 = 0x100,
-    VO_REG = 0x0000, VO_DPX = 0x1000
+    VO_REG = 0x0000, VO_DPX = 0x1000,
+    /* extension (not a reference option value): the tie rule the reference's DPX code paths define (viterbiACS.cuh:101-110,
+     * 123-134,205-213,224-236) but which the reference never instantiates, because viterbi_core does not forward compMode to
+     * forwardACS (viterbi.cu:181,192,204).  int16x2: same as REG.  int32: the partner/even predecessor wins ties for the
+     * u=1 state at phase 0 too (REG: the odd one).  Pinned by oracle/_ref/libvitref_dpx.so, a build of the reference sources
+     * with the flag forwarded (oracle/ref_dpx_shim.cu). */
+    VO_DPX_TIES = 0x2000
 };
 
 /* flags for vo_decode */

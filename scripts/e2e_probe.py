@@ -10,7 +10,7 @@ import torch  # noqa: E402
 opt, n, reps = int(sys.argv[1], 16), int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 20
 V = bench.load_pkg()
 dev = torch.device("cuda", 0)
-bits, packed, N = bench.make_stream_device(torch, n, opt & 0xF, 15.0, 1, dev)
+packed, N = bench.make_stream_device(V, torch, n, opt & 0xF, 15.0, 1, dev)
 dec = V.ViterbiCUDA(opt, N)
 in_bytes, out_bytes = dec.getInputSize(N), dec.getOutputSize(N)
 h_in = packed[:in_bytes].cpu().pin_memory()

@@ -90,6 +90,7 @@ void run_lane_in(int lane) {
 void fiber_main(int lane) {
     switch (g_job.met) {
         case vitk::MET_B32: run_lane_in<vitk::MET_B32>(lane); break;
+        case vitk::MET_B32D: run_lane_in<vitk::MET_B32D>(lane); break;
         case vitk::MET_B16: run_lane_in<vitk::MET_B16>(lane); break;
         default: run_lane_in<vitk::MET_F16>(lane); break;
     }
@@ -126,7 +127,7 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     g_job.kp.in_stride = in_stride; g_job.kp.out_stride = out_stride;
     g_job.kp.in_bytes = in_bytes; g_job.kp.packs = M / bpp;
     g_job.kp.segments = segments; g_job.kp.seg_first = 0; g_job.kp.seg_limit = segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u;
-    g_job.met = mt == 0 ? vitk::MET_B32 : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
+    g_job.met = mt == 0 ? (((options >> 12) & 0xf) == 2 ? vitk::MET_B32D : vitk::MET_B32) : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
     g_job.in = it; g_job.bpp = bpp;
     g_job.smem = (uint8_t*)aligned_alloc(128, 64 * 1024);
     const unsigned spw = 32 / g_job.lanes;

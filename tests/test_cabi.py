@@ -43,15 +43,16 @@ def test_library_contains_sm100a_code():
 
 def test_size_helpers_and_option_table(V, O):
     L = V.lib()
-    for opt in range(0, 0x2000):
+    for opt in range(0, 0x4000):
         it, mt, ot, cm = opt & 0xF, (opt >> 4) & 0xF, (opt >> 8) & 0xF, (opt >> 12) & 0xF
-        known = it <= 4 and mt <= 2 and ot <= 1 and cm <= 1
+        known = it <= 4 and mt <= 2 and ot <= 1 and cm <= 2
         if not known:
             assert not L.vit_options_valid(opt)
             continue
         assert bool(L.vit_options_valid_ref(opt)) == bool(O.lib().vo_options_valid_ref(opt))
-        # ours: superset (f16 x s8/s16 allowed, any comp mode); b16 x s16 rejected as in the reference
-        assert bool(L.vit_options_valid(opt)) == (not (mt == 1 and it == 3))
+        # ours: superset (f16 x s8/s16 allowed, dpx = reg, plus the DPX tie rule as CompMode 2 for the integer cores);
+        # b16 x s16 rejected as in the reference
+        assert bool(L.vit_options_valid(opt)) == (not (mt == 1 and it == 3) and not (cm == 2 and mt == 2))
         for n in (0, 100, 128, 2_000_000, 12_345_679):
             assert L.vit_input_size(opt, n) == O.input_size(opt & 0xFFF, n)
             assert L.vit_message_len(opt, n) == O.message_len(opt & 0xFFF, n)
@@ -73,6 +74,7 @@ def test_parse_options_matches_main_flags(V):
     assert V.parse_options("s4", "b16", "b32") == 0x011
     assert V.parse_options("SOFT8", "f16", "b16") == 0x122
     assert V.parse_options("f", "b32", "b32", "dpx") == 0x1004
+    assert V.parse_options("h", "b32", "b32", "dpxt") == 0x2000
 
 
 def test_no_cpu_fallback_in_product_sources():

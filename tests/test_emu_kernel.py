@@ -95,3 +95,24 @@ def test_kernel_source_long_segments(emu, O, opt):
     amp = {0: 64, 1: 7, 2: 127, 3: 32767, 4: 128}[opt & 0xF]
     run_case(emu, O, opt, 12000 + 64, 4, seed=11, sigma=1.0, amp=amp)
     run_case(emu, O, opt, 12000 + 64, 4, seed=12, sigma=0.2, amp=amp)
+
+
+@pytest.mark.parametrize("opt", [0x2000, 0x2100, 0x2001, 0x2002, 0x2003, 0x2004, 0x2011, 0x2112])
+def test_kernel_source_dpx_tie_rule(emu, O, opt):
+    """CompMode value 2 (extension): the tie rule of the reference's dormant DPX code paths (viterbiACS.cuh:123-134) --
+    int32 core: the partner wins ties in every phase; int16x2 core: identical to REG.  Kernel source vs oracle table."""
+    run_case(emu, O, opt, 3000 + 64 + 7, 12, seed=5, sigma=0.9)
+    run_case(emu, O, opt, 1500 + 64, 5, seed=1, zero=True)             # every compare a tie: output = the tie table
+    emu.vit_emu_set_table(32)
+    try:
+        run_case(emu, O, opt, 1500 + 64, 5, seed=1, zero=True)
+    finally:
+        emu.vit_emu_set_table(96)
+
+
+def test_dpx_tie_rule_differs_from_reg_only_for_int32(O):
+    bits, packed, N = O.make_channel_det(1500 + 64, O.SOFT4, seed=1, zero=True)             # all-zero soft symbols: every compare ties
+    assert not np.array_equal(O.decode(0x2001, packed, N), O.decode(0x0001, packed, N))      # int32: phase-0 ties differ
+    assert np.array_equal(O.decode(0x2011, packed, N), O.decode(0x0011, packed, N))          # int16x2: same table
+    with pytest.raises(ValueError):
+        O.decode(0x2021, packed, N)                                                          # no half2 DPX code

@@ -125,3 +125,23 @@ def test_f16_core_ber_matches_int32_at_noisy_points():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "f16_vs_b32.py"), "2000000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("opt", [0x2000, 0x2100, 0x2001, 0x2002, 0x2003, 0x2004, 0x2011, 0x2012, 0x2110])
+def test_dpx_tie_rule_matches_the_reference_dpx_code(V, O, decoders, opt):
+    """CompMode value 2: this repo's core with the tie rule of the reference's DPX code paths, against those code paths
+    themselves -- oracle/_ref/libvitref_dpx.so is the unmodified reference source compiled with compMode forwarded to
+    forwardACS (oracle/ref_dpx_shim.cu; the stock build never runs them).  All-zero input makes every compare a tie."""
+    it = opt & 0xF
+    n = 6400 * 32 * 2 + 64 + 32 * 99 if it < 3 else 64 + 32 * 5000
+    for sigma, zero, seed in ((1.0, False, 41), (0.0, True, 1), (3.0, False, 7)):
+        bits, packed, N = O.make_channel_det(n, it, seed=seed, sigma=sigma, zero=zero)
+        got = decoders(opt).run(packed, N)
+        assert np.array_equal(got, O.decode(opt, packed, N)), (hex(opt), sigma, zero)
+        if O.ref_dpx_lib() is not None:
+            ref, _ = O.ref_decode_dpx((opt & 0xFFF) | 0x1000, packed, N)
+            m = owned_mask(O, opt & 0xFFF, N, ref.size)
+            assert np.array_equal(got[m], ref[m]), (hex(opt), sigma, zero)
+            if zero and (opt & 0xF0) == 0 and it != 0:       # (all-zero HARD words are valid symbols, not ties)
+                stock, _ = O.ref_decode((opt & 0xFFF) | 0x1000, packed, N)     # the stock reference runs REG code for -c dpx
+                assert not np.array_equal(stock[m], ref[m])
