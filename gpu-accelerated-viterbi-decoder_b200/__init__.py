@@ -94,6 +94,12 @@ def lib():
         L.vit_synth_device_ex.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp, vp]
         L.vit_count_errors_synth_device.restype = C.c_int
         L.vit_count_errors_synth_device.argtypes = [C.c_int, vp, sz, C.c_uint, C.c_int, C.POINTER(C.c_ulonglong), vp]
+        L.vit_stream_reset.restype, L.vit_stream_reset.argtypes = C.c_int, [vp]
+        L.vit_stream_push.restype, L.vit_stream_push.argtypes = C.c_int, [vp, vp, sz, vp, sz, C.POINTER(sz)]
+        L.vit_stream_push_device.restype = C.c_int
+        L.vit_stream_push_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
+        L.vit_stream_pending.restype, L.vit_stream_pending.argtypes = sz, [vp]
+        L.vit_stream_bits.restype, L.vit_stream_bits.argtypes = C.c_ulonglong, [vp]
         L.vit_dev_set.restype, L.vit_dev_set.argtypes = C.c_int, [C.c_int]
         L.vit_dev_copy_to_host.restype, L.vit_dev_copy_to_host.argtypes = C.c_int, [vp, vp, sz]
         L.vit_dev_copy_from_host.restype, L.vit_dev_copy_from_host.argtypes = C.c_int, [vp, vp, sz]
@@ -231,6 +237,27 @@ class ViterbiCUDA:
         _check(lib().vit_run_device_batch(self._h, in_ptr, out_ptr, inputNum, nstreams, in_stride, out_stride,
                                           stream, C.byref(ms) if want_kernel_time else None))
         return ms.value if want_kernel_time else None
+
+    # chunked decode of an endless stream (vit_stream_*): the reference has no equivalent (viterbi.cu:168-169)
+    def stream_reset(self):
+        _check(lib().vit_stream_reset(self._h))
+
+    def stream_push(self, input_h, inputNum):
+        """Append inputNum coded symbols (whole 32-bit channel packs); returns the decoded packs this chunk completes."""
+        input_h = np.ascontiguousarray(input_h)
+        if input_h.nbytes < self.getInputSize(inputNum):
+            raise ViterbiError("input buffer holds %d bytes, %d needed" % (input_h.nbytes, self.getInputSize(inputNum)))
+        cap = self.getOutputSize(self.stream_pending() + inputNum)
+        out = np.empty(cap // np.dtype(self.decPack_t).itemsize, self.decPack_t)
+        n = C.c_size_t(0)
+        _check(lib().vit_stream_push(self._h, input_h.ctypes.data, int(inputNum), out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value // np.dtype(self.decPack_t).itemsize]
+
+    def stream_pending(self):
+        return int(lib().vit_stream_pending(self._h))
+
+    def stream_bits(self):
+        return int(lib().vit_stream_bits(self._h))
 
     def set_upload_mode(self, mode):
         """UPLOAD_AUTO / _SEQUENTIAL / _CHUNKED / _GATED: how run() moves host buffers (vit_set_upload_mode)."""

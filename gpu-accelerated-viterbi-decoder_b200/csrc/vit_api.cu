@@ -239,6 +239,10 @@ struct vit_handle {
     // when every stream shares one hardware queue (CUDA_DEVICE_MAX_CONNECTIONS=1) or when launches block the host
     // (CUDA_LAUNCH_BLOCKING=1): detected up front, vit_run then takes the segment-range chunk pipeline.
     bool gates_disabled = env_forbids_gates();
+    // chunked decode of an endless stream (vit_stream_push): the symbols of the previous window that could not be
+    // decoded yet (its last 64..64+bitsPerPack-1 stages) wait here and are prepended to the next chunk
+    void* carry_d = nullptr; size_t carry_cap = 0; size_t carry_syms = 0;
+    unsigned long long stream_bits = 0;   // bits emitted since vit_stream_reset
     int upload_mode = VIT_UPLOAD_AUTO;    // vit_set_upload_mode
     unsigned long long gate_timeout_ns = 2000000000ull;
     StagePool* pool = nullptr;            // created on the first vit_run with pageable buffers
@@ -381,6 +385,7 @@ bool gated_upload_applies(const vit_handle* h, const HostRun& g) {
 int ensure_staging(vit_handle* h, size_t in_bytes, size_t out_bytes) {
     if (in_bytes > h->pin_in_cap) {
         delete h->pool;
+    if (h->carry_d) cudaFree(h->carry_d);
     if (h->pin_in) cudaFreeHost(h->pin_in);
         h->pin_in = nullptr; h->pin_in_cap = 0;
         VIT_CUDA(cudaHostAlloc(&h->pin_in, in_bytes + 256, cudaHostAllocDefault));
@@ -660,6 +665,7 @@ void vit_destroy(vit_handle* h) {
     if (h->in_d) cudaFree(h->in_d);
     if (h->out_d) cudaFree(h->out_d);
     delete h->pool;
+    if (h->carry_d) cudaFree(h->carry_d);
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -731,6 +737,73 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
     if (!pin_in || !pin_out || hr.nch < 2) return run_sequential(h, hr, nullptr);
     return run_chunked(h, hr);
 }
+
+// ---- chunked decode of an endless stream ---------------------------------------------------------
+namespace {
+size_t symbols_per_word(int o) { return in_type(o) == 0 ? 32 : in_type(o) == 1 ? 8 : in_type(o) == 2 ? 4 : in_type(o) == 3 ? 2 : 1; }
+
+// One window = carried symbols ++ this chunk.  `chunk` is a host pointer (chunk_on_device == false) or a device pointer.
+int stream_push(vit_handle* h, const void* chunk, bool chunk_on_device, size_t inputNum, void* out, bool out_on_device,
+                size_t out_cap, size_t* out_bytes, cudaStream_t st) {
+    const int o = h->options;
+    if (inputNum % symbols_per_word(o))
+        return fail(VIT_ERR_ARG, "a stream chunk must be whole 32-bit channel packs (%zu symbols per pack, got %zu symbols)", symbols_per_word(o), inputNum);
+    const size_t n = h->carry_syms + inputNum;
+    const size_t carry_bytes = vit_input_size(o, h->carry_syms), chunk_bytes = vit_input_size(o, inputNum), win_bytes = carry_bytes + chunk_bytes;
+    const size_t M = vit_message_len(o, n), need_out = M / 8;
+    if (out_bytes) *out_bytes = 0;
+    if (need_out > out_cap) return fail(VIT_ERR_ARG, "this chunk completes %zu bytes of decoded packs, the output buffer holds %zu", need_out, out_cap);
+    int rc = ensure_device_buffers(h, win_bytes + 16, need_out);
+    if (rc) return rc;
+    char* win = static_cast<char*>(h->in_d);
+    if (carry_bytes) VIT_CUDA(cudaMemcpyAsync(win, h->carry_d, carry_bytes, cudaMemcpyDeviceToDevice, st));
+    if (chunk_bytes) VIT_CUDA(cudaMemcpyAsync(win + carry_bytes, chunk, chunk_bytes, chunk_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (M) {
+        void* out_d = out_on_device ? out : h->out_d;
+        rc = launch(h, win, out_d, n, 1, 0, 0, st, nullptr);
+        if (rc) return rc;
+        if (!out_on_device) VIT_CUDA(cudaMemcpyAsync(out, h->out_d, need_out, cudaMemcpyDeviceToHost, st));
+    }
+    // the next window starts at stage M of this one: its first decoded bit is then message bit M + 26 of this window,
+    // the bit after the last one emitted now
+    const size_t tail_off = vit_input_size(o, 2 * M), tail_bytes = win_bytes - tail_off;
+    if (tail_bytes > h->carry_cap) {
+        void* p = nullptr;
+        VIT_CUDA(cudaMalloc(&p, tail_bytes + 1024));
+        VIT_CUDA(cudaStreamSynchronize(st));
+        if (h->carry_d) cudaFree(h->carry_d);
+        h->carry_d = p; h->carry_cap = tail_bytes + 1024;
+    }
+    if (tail_bytes) VIT_CUDA(cudaMemcpyAsync(h->carry_d, win + tail_off, tail_bytes, cudaMemcpyDeviceToDevice, st));
+    h->carry_syms = n - 2 * M;
+    h->stream_bits += M;
+    if (out_bytes) *out_bytes = need_out;
+    if (!out_on_device || !chunk_on_device) VIT_CUDA(cudaStreamSynchronize(st));
+    return VIT_OK;
+}
+}  // namespace
+
+int vit_stream_reset(vit_handle* h) {
+    if (!h) return fail(VIT_ERR_ARG, "null handle");
+    h->carry_syms = 0; h->stream_bits = 0;
+    return VIT_OK;
+}
+
+int vit_stream_push(vit_handle* h, const void* in_h, size_t inputNum, void* out_h, size_t out_cap, size_t* out_bytes) {
+    if (!h || (!in_h && inputNum) || (!out_h && out_cap)) return fail(VIT_ERR_ARG, "null argument");
+    VIT_ON_DEVICE(h);
+    return stream_push(h, in_h, false, inputNum, out_h, false, out_cap, out_bytes, h->stream);
+}
+
+int vit_stream_push_device(vit_handle* h, const void* in_d, size_t inputNum, void* out_d, size_t out_cap, size_t* out_bytes,
+                           void* cuda_stream) {
+    if (!h || (!in_d && inputNum) || (!out_d && out_cap)) return fail(VIT_ERR_ARG, "null argument");
+    VIT_ON_DEVICE(h);
+    return stream_push(h, in_d, true, inputNum, out_d, true, out_cap, out_bytes, static_cast<cudaStream_t>(cuda_stream));
+}
+
+size_t vit_stream_pending(const vit_handle* h) { return h ? h->carry_syms : 0; }
+unsigned long long vit_stream_bits(const vit_handle* h) { return h ? h->stream_bits : 0; }
 
 int vit_set_upload_mode(vit_handle* h, int mode) {
     if (!h) return fail(VIT_ERR_ARG, "null handle");

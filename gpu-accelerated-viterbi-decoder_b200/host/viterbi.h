@@ -126,6 +126,15 @@ public:
         VIT_HANDLE_ERROR(vit_run_device_batch(h_, in_d, out_d, inputNum, nstreams, inStride, outStride, stream, kernelTime));
     }
 
+    // chunked decode of an endless stream (new: vit_stream_* in include/vit_b200.h); returns the bytes written to output_h
+    void streamReset() { VIT_HANDLE_ERROR(vit_stream_reset(h_)); }
+    size_t streamPush(const encPack_t* input_h, size_t inputNum, decPack_t* output_h, size_t outputCapacityBytes) {
+        size_t written = 0;
+        VIT_HANDLE_ERROR(vit_stream_push(h_, input_h, inputNum, output_h, outputCapacityBytes, &written));
+        return written;
+    }
+    size_t streamPending() const { return vit_stream_pending(h_); }
+
     size_t getInputSize(size_t inputNum) { return vit_input_size(options, inputNum); }      // viterbi.cu:63-84
     size_t getMessageLen(size_t inputNum) { return vit_message_len(options, inputNum); }    // viterbi.cu:86-88
     size_t getOutputSize(size_t inputNum) { return vit_output_size(options, inputNum); }    // viterbi.cu:90-92

@@ -89,6 +89,25 @@ int vit_run_device_batch(vit_handle* h, const void* in_d, void* out_d, size_t in
                          size_t nstreams, size_t in_stride, size_t out_stride,
                          void* cuda_stream, float* kernel_ms);
 
+/* Chunked decode of an endless stream (new; SURVEY.md 8f: the reference decodes one buffer per run() and restarts from
+ * all-zero metrics every call, viterbi.cu:168-169, so consecutive calls lose 64 stages at every seam).
+ * Every push appends `inputNum` coded symbols (whole 32-bit channel packs) to the stream.  The decoder forms the window
+ * "symbols carried from the previous push ++ this chunk", decodes it exactly as vit_run would (same 6400-segment
+ * partition OF THE WINDOW, same warm-up, same tie rules: bit-identical to the reference's run() on that window), emits
+ * M = ((window stages - 64) / bitsPerPack) * bitsPerPack bits and carries the window's symbols from stage M on (64 to
+ * 64 + bitsPerPack - 1 stages, kept on the device) into the next window.  Window k+1 therefore starts at stage M of
+ * window k and its first decoded bit is the one after window k's last: the concatenated outputs are the contiguous
+ * message bits 26, 27, ... of the endless stream, and equal a one-shot decode of the concatenated input in which the
+ * segment partition is applied per window.  The last 38..69 stages pushed are always pending (the reference likewise
+ * never decodes its last extraR bits).  out_cap: capacity of the output buffer in bytes; *out_bytes: bytes written. */
+int vit_stream_reset(vit_handle* h);
+int vit_stream_push(vit_handle* h, const void* in_h, size_t inputNum, void* out_h, size_t out_cap, size_t* out_bytes);
+/* device-resident chunk and output (out_d aligned to its packs); asynchronous on cuda_stream */
+int vit_stream_push_device(vit_handle* h, const void* in_d, size_t inputNum, void* out_d, size_t out_cap,
+                           size_t* out_bytes, void* cuda_stream);
+size_t vit_stream_pending(const vit_handle* h);            /* carried coded symbols */
+unsigned long long vit_stream_bits(const vit_handle* h);   /* bits emitted since vit_stream_reset */
+
 /* replace getInputSize / getMessageLen / getOutputSize (viterbi.cu:63-92); bytes, bits, bytes */
 size_t vit_input_size(int options, size_t inputNum);
 size_t vit_message_len(int options, size_t inputNum);

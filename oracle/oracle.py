@@ -118,6 +118,28 @@ def decode_window(options, in_window, input_num, seg_begin, seg_end, nthreads=0)
     return w0, out
 
 
+def decode_chunked(options, packed, chunk_syms, flags=0):
+    """Restatement of the chunked stream decode (C ABI vit_stream_push): window k = symbols carried from window k-1 ++
+    chunk k, decoded like a one-shot run() of that window; carry = the window from stage M_k on.  packed: the whole
+    stream's channel words; chunk_syms: coded symbols per push (each a whole number of 32-bit packs).
+    Returns (list of per-push outputs, pending symbols)."""
+    it = options & 0xF
+    spw = {HARD: 32, SOFT4: 8, SOFT8: 4, SOFT16: 2, FP32: 1}[it]
+    words = np.ascontiguousarray(packed).view(np.uint32)
+    bpp = 16 if (options & 0xF00) == O_B16 else 32
+    outs, start, fed = [], 0, 0                 # start: first symbol of the current window
+    for c in chunk_syms:
+        assert c % spw == 0
+        fed += c
+        n = fed - start
+        M = message_len(options, n)
+        w = words[start // spw: fed // spw]
+        outs.append(decode(options, w, n, flags=flags) if M else np.zeros(0, out_dtype(options)))
+        start += 2 * M
+        assert M % bpp == 0
+    return outs, fed - start
+
+
 def overrun_words(options, input_num):
     n = lib().vo_overrun_words(options, input_num, None, 0)
     idx = np.zeros(max(n, 1), np.uint64)
