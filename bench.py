@@ -56,7 +56,6 @@ BYTES_PER_BIT_IN = {0: 0.25, 1: 1.0, 2: 2.0, 3: 4.0, 4: 8.0}
 NCU_DRAM_BYTES = {
     ("s4_b16_o32_32M", 1): (32.03e6, "profiles/r1_v7_ncu_core_0x011.txt"),
 }
-DEFAULT_STEP_GATHER = "direct"
 N_SM = 148
 
 
@@ -399,9 +398,9 @@ def main():
     ap.add_argument("--workload", default="s4_b16_o32_32M", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=1, help="independent codeword streams decoded per step by ONE launch; config5: streams of the whole job (default 1024)")
     ap.add_argument("--gather", default=None, choices=["nccl", "copy", "direct", "none"],
-                    help="N > 1: how the packed output bits reach rank 0 (default: nccl for config5, direct for the per-step bench)")
-    ap.add_argument("--wave", type=int, default=16, help="config5: streams per decode launch")
-    ap.add_argument("--batch", type=int, default=32, help="config5: streams generated ahead of each timed decode phase")
+                    help="N > 1: how the packed output bits reach rank 0 (default: copy for config5; per-step bench: direct up to 4 GPUs, copy beyond)")
+    ap.add_argument("--wave", type=int, default=8, help="config5: streams per decode launch (the last wave's gather is the exposed tail of a round)")
+    ap.add_argument("--batch", type=int, default=64, help="config5: streams generated ahead of each timed decode phase (one gather tail per round)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -426,12 +425,14 @@ def main():
 
     V = load_pkg()
     if args.workload == "config5":
-        args.gather = args.gather or "nccl"
+        args.gather = args.gather or "copy"
         run_config5(args, V, torch, dist, rank, world, local, dev)
         if world > 1:
             dist.destroy_process_group()
         return
-    args.gather = args.gather or DEFAULT_STEP_GATHER
+    # direct stores scale to a fan-in of 3 senders (99.4-99.7 % of N x one GPU at N = 2, 4); with 7 senders the root's NVLink
+    # ingress saturates on 4-byte packets (52 % at N = 8), where the copy-engine gather keeps 96 % (profiles/bench_r2/scale8)
+    args.gather = args.gather or ("direct" if world <= 4 else "copy")
     it, bpp = options & 0xF, (16 if options & 0x100 else 32)
     dec = V.ViterbiCUDA(options, 2 * n_bits, device=local)
     N = 2 * n_bits
@@ -459,6 +460,7 @@ def main():
     #   nccl   one grouped ncclSend/ncclRecv per GB steps (NCCL kernels beside the decode kernel)
     #   direct the decode kernel stores its packs straight into rank 0's buffer over NVLink
     GB = 8 if world > 1 else 1
+    CG = 2                                                  # steps per copy-engine transfer (divides GB)
     out_stride1 = (out_bytes + 255) // 256 * 256          # per stream
     out_stride = out_stride1 * S                            # per step
     ring_bytes = 2 * GB * out_stride
@@ -473,25 +475,35 @@ def main():
             return root_buf + rank * ring_bytes + slot * out_stride      # rank 0's buffer, mapped into this process
         return ring.data_ptr() + slot * out_stride
 
+    arrays = {}
+
     def gather_slots(slot0, nslots):
-        offs = [p * ring_bytes + slot0 * out_stride for p in range(world)]
-        comm.gatherv(state["gather"], ring.data_ptr() + slot0 * out_stride, root_buf, offs, [nslots * out_stride] * world, 0, st.cuda_stream)
+        key = (slot0, nslots)
+        if key not in arrays:
+            arrays[key] = (comm.size_array([p * ring_bytes + slot0 * out_stride for p in range(world)]), comm.size_array([nslots * out_stride] * world))
+        offs, sizes = arrays[key]
+        comm.gatherv(state["gather"], ring.data_ptr() + slot0 * out_stride, root_buf, offs, sizes, 0, st.cuda_stream)
 
     def step(k):
         slot = k % (2 * GB)
+        h = slot // GB
         if comm is not None and slot % GB == 0 and state["gather"] in (V.GATHER_NCCL, V.GATHER_COPY):
-            comm.stream_wait(st.cuda_stream)   # the gathers that read this half of the ring were issued 2*GB steps ago
+            comm.stream_wait_mark(h, st.cuda_stream)   # the gathers that read this half of the ring (issued GB..2*GB steps ago) are done
         dec.run_device(streams[k % nbuf].data_ptr(), out_ptr(slot), N, stream=st.cuda_stream,
                        nstreams=S, in_stride=in_stride, out_stride=out_stride1)
         if state["gather"] == V.GATHER_COPY:
-            gather_slots(slot, 1)
+            if slot % CG == CG - 1:
+                gather_slots(slot - CG + 1, CG)        # one copy-engine transfer per CG steps
         elif state["gather"] == V.GATHER_NCCL and slot % GB == GB - 1:
             gather_slots(slot - GB + 1, GB)
+        if comm is not None and slot % GB == GB - 1 and state["gather"] in (V.GATHER_NCCL, V.GATHER_COPY):
+            comm.mark(h)
 
     def flush_partial(last_k):
-        if state["gather"] == V.GATHER_NCCL and (last_k % GB) != GB - 1:
+        g = GB if state["gather"] == V.GATHER_NCCL else CG if state["gather"] == V.GATHER_COPY else 0
+        if g and (last_k % g) != g - 1:
             slot = last_k % (2 * GB)
-            gather_slots(slot - slot % GB, slot % GB + 1)                # partial group at the end of a run
+            gather_slots(slot - slot % g, slot % g + 1)                  # partial group at the end of a run
 
     def drain(last_k=None):
         if last_k is not None:

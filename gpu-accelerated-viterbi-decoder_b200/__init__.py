@@ -113,6 +113,8 @@ def lib():
         L.vit_comm_size.restype, L.vit_comm_size.argtypes = C.c_int, [vp]
         L.vit_comm_barrier.restype, L.vit_comm_barrier.argtypes = C.c_int, [vp]
         L.vit_comm_stream_wait.restype, L.vit_comm_stream_wait.argtypes = C.c_int, [vp, vp]
+        L.vit_comm_mark.restype, L.vit_comm_mark.argtypes = C.c_int, [vp, C.c_int]
+        L.vit_comm_stream_wait_mark.restype, L.vit_comm_stream_wait_mark.argtypes = C.c_int, [vp, C.c_int, vp]
         L.vit_comm_stream.restype, L.vit_comm_stream.argtypes = vp, [vp]
         L.vit_shard_range.restype, L.vit_shard_range.argtypes = None, [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
         L.vit_shard_owner.restype, L.vit_shard_owner.argtypes = C.c_int, [sz, C.c_int, sz]
@@ -320,15 +322,24 @@ class Comm:
     def stream_wait(self, stream):
         _check(lib().vit_comm_stream_wait(self._c, stream))
 
+    def mark(self, k):
+        _check(lib().vit_comm_mark(self._c, int(k)))
+
+    def stream_wait_mark(self, k, stream):
+        _check(lib().vit_comm_stream_wait_mark(self._c, int(k), stream))
+
     def shared_alloc(self, nbytes, root=0):
         p = C.c_void_p()
         _check(lib().vit_comm_shared_alloc(self._c, C.byref(p), int(nbytes), int(root)))
         return p.value
 
+    def size_array(self, values):
+        """a per-rank size_t array for gatherv (build once, reuse every step)"""
+        return (C.c_size_t * self.nranks)(*[int(x) for x in values])
+
     def gatherv(self, mode, send_ptr, recv_base, offsets, sizes, root=0, producer_stream=0):
-        n = self.nranks
-        off = (C.c_size_t * n)(*[int(x) for x in offsets])
-        siz = (C.c_size_t * n)(*[int(x) for x in sizes])
+        off = offsets if isinstance(offsets, C.Array) else self.size_array(offsets)
+        siz = sizes if isinstance(sizes, C.Array) else self.size_array(sizes)
         _check(lib().vit_comm_gatherv(self._c, int(mode), send_ptr, recv_base, off, siz, int(root), producer_stream))
 
     def close(self):

@@ -114,6 +114,8 @@ struct vit_comm {
     int peer_devices[64] = {};           // single_process: device ordinal of every rank
     cudaStream_t gstream = nullptr;      // gathers run here, beside the decode stream
     cudaEvent_t ev_prod = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_mark[8] = {};         // vit_comm_mark / vit_comm_stream_wait_mark
+    bool mark_set[8] = {};
     int* scratch_d = nullptr;            // barrier word + IPC handle exchange
     struct Shared { void* ptr; bool mapped; };
     std::vector<Shared> shared;          // vit_comm_shared_alloc results (root: owned, peers: IPC mappings)
@@ -130,6 +132,7 @@ int comm_finish_init(vit_comm* c) {
     MG_CUDA(cudaStreamCreateWithPriority(&c->gstream, cudaStreamNonBlocking, hi));
     MG_CUDA(cudaEventCreateWithFlags(&c->ev_prod, cudaEventDisableTiming));
     MG_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    for (auto& e : c->ev_mark) MG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     MG_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->scratch_d), 256));
     MG_CUDA(cudaMemset(c->scratch_d, 0, 256));
     return VIT_OK;
@@ -250,6 +253,7 @@ void vit_comm_destroy(vit_comm* c) {
     if (c->gstream) cudaStreamDestroy(c->gstream);
     if (c->ev_prod) cudaEventDestroy(c->ev_prod);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
+    for (auto e : c->ev_mark) if (e) cudaEventDestroy(e);
     if (c->scratch_d) cudaFree(c->scratch_d);
     if (c->comm && nccl()) nccl()->CommDestroy(c->comm);
     delete c;
@@ -293,6 +297,26 @@ int vit_comm_stream_wait(vit_comm* c, void* stream) {
     DevGuard g(c->device);
     MG_CUDA(cudaEventRecord(c->ev_done, c->gstream));
     MG_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->ev_done, 0));
+    return VIT_OK;
+}
+
+// Markers: vit_comm_mark(k) remembers the point the gather stream has reached (after the gathers issued so far);
+// vit_comm_stream_wait_mark(k) makes `stream` wait for that point only -- unlike vit_comm_stream_wait it does not wait
+// for gathers issued after the mark (e.g. the one that is still reading the slot decoded a moment ago).
+int vit_comm_mark(vit_comm* c, int k) {
+    if (!c) return VIT_OK;
+    if (k < 0 || k >= 8) return mg_fail(VIT_ERR_ARG, "marker index out of range");
+    DevGuard g(c->device);
+    MG_CUDA(cudaEventRecord(c->ev_mark[k], c->gstream));
+    c->mark_set[k] = true;
+    return VIT_OK;
+}
+int vit_comm_stream_wait_mark(vit_comm* c, int k, void* stream) {
+    if (!c) return VIT_OK;
+    if (k < 0 || k >= 8) return mg_fail(VIT_ERR_ARG, "marker index out of range");
+    if (!c->mark_set[k]) return VIT_OK;
+    DevGuard g(c->device);
+    MG_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->ev_mark[k], 0));
     return VIT_OK;
 }
 

@@ -29,9 +29,9 @@ struct Args {
     int streams = 1;
     int gpus = 1;
     bool deviceSource = false;      // generate, decode and count errors on the device (no host pipeline)
-    std::string gather = "nccl";    // how the stream job brings the packed output bits to GPU 0
-    int wave = 16;                  // streams per decode launch
-    int batch = 32;                 // streams generated ahead of each timed decode phase
+    std::string gather = "copy";    // how the stream job brings the packed output bits to GPU 0
+    int wave = 8;                   // streams per decode launch
+    int batch = 64;                 // streams generated ahead of each timed decode phase
 };
 
 static void usage(const char* prog) {
@@ -51,10 +51,10 @@ static void usage(const char* prog) {
               << "      --streams <integer>  Stream job: independent streams of -n bits, generated on the device,\n"
               << "                           sharded over --gpus in contiguous blocks, outputs gathered to GPU 0.\n"
               << "      --gpus <integer>     Number of GPUs (one decoder, one communicator and one host thread per GPU).\n"
-              << "      --gather <mode>      nccl (ncclSend/ncclRecv per finished wave, default) | copy (copy engines) |\n"
+              << "      --gather <mode>      copy (copy engines over NVLink per finished wave, default) | nccl (ncclSend/ncclRecv) |\n"
               << "                           direct (the kernel stores into GPU 0's buffer over NVLink) | none.\n"
-              << "      --wave <integer>     Streams per decode launch (default 16).\n"
-              << "      --batch <integer>    Streams generated ahead of each timed decode phase (default 32).\n"
+              << "      --wave <integer>     Streams per decode launch (default 8).\n"
+              << "      --batch <integer>    Streams generated ahead of each timed decode phase (default 64).\n"
               << "      --device-source      Generate the channel, decode and count bit errors on the device\n"
               << "                           (counter-based source; needed for multi-Gbit -n, e.g. -n 4000000000 -i f).\n"
               << "  -h, --help               Display this help message.\n";

@@ -190,6 +190,9 @@ int vit_comm_size(const vit_comm* c);
 int vit_comm_barrier(vit_comm* c);
 /* make a stream wait for the gathers this rank has issued so far */
 int vit_comm_stream_wait(vit_comm* c, void* cuda_stream);
+/* markers 0..7: remember how far the gather stream has got / make a stream wait for that point only (output-slot rings) */
+int vit_comm_mark(vit_comm* c, int k);
+int vit_comm_stream_wait_mark(vit_comm* c, int k, void* cuda_stream);
 /* the stream the gathers run on (a cudaStream_t) */
 void* vit_comm_stream(vit_comm* c);
 
