@@ -13,13 +13,10 @@ import torch  # noqa: E402
 opt, n, reps = int(sys.argv[1], 16), int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 3
 V = bench.load_pkg()
 dev = torch.device("cuda", 0)
-bits, packed, N = bench.make_stream_device(torch, n, opt & 0xF, 15.0, 1, dev)
-pad = (-packed.numel()) % 256
-if pad:
-    packed = torch.cat([packed, torch.zeros(pad, dtype=torch.uint8, device=dev)])
+packed, N = bench.make_stream_device(V, torch, n, opt & 0xF, 15.0, 1, dev)
 dec = V.ViterbiCUDA(opt, N)
 out = torch.zeros(dec.getOutputSize(N) + 256, dtype=torch.uint8, device=dev)
 ms = [dec.run_device(packed.data_ptr(), out.data_ptr(), N, want_kernel_time=True) for _ in range(reps)]
-errs = bench.count_errors_device(torch, out, bits, dec.getMessageLen(N), 16 if opt & 0x100 else 32)
+errs = V.count_errors_synth_device(opt, out.data_ptr(), dec.getMessageLen(N), seed=1, source=V.SOURCE_PRBS31)
 print("options %#x  n=%d  kernel ms %s  -> %.1f Gb/s  bit errors %d" % (opt, n, ["%.3f" % m for m in ms], dec.getMessageLen(N) / min(ms) / 1e6, errs))
 sys.exit(1 if errs else 0)
