@@ -28,7 +28,7 @@ done
 echo "== per-step bench at N=$MAX, other gather modes"
 if has modes && [ $MAX -gt 1 ]; then
   for g in ${MODES:-nccl copy direct none}; do run step_n${MAX}_$g trun $MAX bench.py --gpus $MAX --steps 200 --warmup 5 --gather $g --no-e2e; done
-  VIT_NCCL_MAX_CTAS=2 run step_n${MAX}_nccl_cta2 trun $MAX bench.py --gpus $MAX --steps 200 --warmup 5 --gather nccl --no-e2e
+  case " ${MODES:-nccl} " in *" nccl "*) VIT_NCCL_MAX_CTAS=2 run step_n${MAX}_nccl_cta2 trun $MAX bench.py --gpus $MAX --steps 200 --warmup 5 --gather nccl --no-e2e;; esac
   export VIT_NCCL_MAX_CTAS=; unset VIT_NCCL_MAX_CTAS
 fi
 echo "== config 5: $STREAMS streams x 256 Mbit s8 / int16x2"
