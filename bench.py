@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--workload", default="s4_b16_o32_32M", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=1, help="independent codeword streams decoded per step by ONE launch; config5: streams of the whole job (default 1024)")
     ap.add_argument("--gather", default=None, choices=["nccl", "copy", "direct", "none"],
-                    help="N > 1: how the packed output bits reach rank 0 (default: copy for config5; per-step bench: direct up to 4 GPUs, copy beyond)")
+                    help="N > 1: how the packed output bits reach rank 0 (default: direct)")
     ap.add_argument("--wave", type=int, default=8, help="config5: streams per decode launch (the last wave's gather is the exposed tail of a round)")
     ap.add_argument("--batch", type=int, default=64, help="config5: streams generated ahead of each timed decode phase (one gather tail per round)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -425,14 +425,15 @@ def main():
 
     V = load_pkg()
     if args.workload == "config5":
-        args.gather = args.gather or "copy"
+        args.gather = args.gather or "direct"
         run_config5(args, V, torch, dist, rank, world, local, dev)
         if world > 1:
             dist.destroy_process_group()
         return
-    # direct stores scale to a fan-in of 3 senders (99.4-99.7 % of N x one GPU at N = 2, 4); with 7 senders the root's NVLink
-    # ingress saturates on 4-byte packets (52 % at N = 8), where the copy-engine gather keeps 96 % (profiles/bench_r2/scale8)
-    args.gather = args.gather or ("direct" if world <= 4 else "copy")
+    # direct stores: nothing runs but the decode kernel, which stages 8 slides per segment and stores 32 bytes at a time into
+    # rank 0's buffer over NVLink: 99.0-99.7 % of N x one GPU at N = 2, 4, 8 (copy engines: 95 %, NCCL send/recv: 89 %;
+    # profiles/bench_r2/scale8_staged, scale8)
+    args.gather = args.gather or "direct"
     it, bpp = options & 0xF, (16 if options & 0x100 else 32)
     dec = V.ViterbiCUDA(options, 2 * n_bits, device=local)
     N = 2 * n_bits

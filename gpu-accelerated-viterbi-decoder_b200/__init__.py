@@ -100,6 +100,8 @@ def lib():
         L.vit_stream_push_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
         L.vit_stream_pending.restype, L.vit_stream_pending.argtypes = sz, [vp]
         L.vit_stream_bits.restype, L.vit_stream_bits.argtypes = C.c_ulonglong, [vp]
+        L.vit_depuncture_device.restype = C.c_int
+        L.vit_depuncture_device.argtypes = [C.c_int, vp, sz, C.c_uint, C.c_uint, C.c_uint, vp, sz, vp]
         L.vit_dev_set.restype, L.vit_dev_set.argtypes = C.c_int, [C.c_int]
         L.vit_dev_copy_to_host.restype, L.vit_dev_copy_to_host.argtypes = C.c_int, [vp, vp, sz]
         L.vit_dev_copy_from_host.restype, L.vit_dev_copy_from_host.argtypes = C.c_int, [vp, vp, sz]
@@ -282,6 +284,18 @@ class ViterbiCUDA:
 
 # ---------------------------------------------------------------------------------------------------------------------
 # multi-GPU: stream sharding + gather of the packed output bits (C ABI vit_comm_* / vit_job_*, csrc/vit_mg.cu)
+
+# standard puncturing patterns of the K=7 (171,133) mother code (DVB-S / 802.11): (period, keep0, keep1)
+PUNCTURE = {"1/2": (1, 0b1, 0b1), "2/3": (2, 0b01, 0b11), "3/4": (3, 0b101, 0b011), "5/6": (5, 0b10101, 0b01011), "7/8": (7, 0b1010001, 0b0101111)}
+
+
+def depuncture_device(input_type, in_ptr, n_in_syms, rate, out_ptr, n_out_stages, stream=0):
+    """Expand a punctured soft-symbol stream to rate 1/2 with erasures (vit_depuncture_device).  rate: a key of PUNCTURE or
+    a (period, keep0, keep1) tuple."""
+    period, k0, k1 = PUNCTURE[rate] if isinstance(rate, str) else rate
+    _check(lib().vit_depuncture_device(int(input_type), in_ptr, int(n_in_syms), int(period), int(k0), int(k1), out_ptr,
+                                       int(n_out_stages), stream))
+
 
 def dev_to_host(src_ptr, nbytes):
     """nbytes of device memory at src_ptr as a numpy uint8 array (synchronous copy)."""

@@ -243,6 +243,8 @@ struct vit_handle {
     // decoded yet (its last 64..64+bitsPerPack-1 stages) wait here and are prepended to the next chunk
     void* carry_d = nullptr; size_t carry_cap = 0; size_t carry_syms = 0;
     unsigned long long stream_bits = 0;   // bits emitted since vit_stream_reset
+    const void* remote_checked = nullptr; bool remote_is = false;   // last output pointer examined for "lives on another GPU"
+    bool force_stage_out = getenv("VIT_STAGE_OUT") != nullptr;       // measurement hook: staged output stores for local buffers too
     int upload_mode = VIT_UPLOAD_AUTO;    // vit_set_upload_mode
     unsigned long long gate_timeout_ns = 2000000000ull;
     StagePool* pool = nullptr;            // created on the first vit_run with pageable buffers
@@ -292,6 +294,17 @@ int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, 
     kp.one = 1u;
     kp.gate = h->gate_d; kp.gate_err = h->gate_err_d; kp.gate_epoch = h->epoch; kp.gate_n = 0;
     kp.gate_timeout_ns = h->gate_timeout_ns;
+    // output in another GPU's memory (a peer / IPC mapping: VIT_GATHER_DIRECT): the kernel stages 8 slides per store
+    kp.stage_out = 0;
+    if (out_d != h->out_d) {
+        if (out_d != h->remote_checked) {
+            cudaPointerAttributes pa;
+            h->remote_is = cudaPointerGetAttributes(&pa, out_d) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->device;
+            cudaGetLastError();
+            h->remote_checked = out_d;
+        }
+        kp.stage_out = (h->remote_is || h->force_stage_out) ? 1u : 0u;
+    }
     for (int i = 0; i < 8; i++) kp.gate_super[i] = 0;
     if (gp && h->gate_d) {
         kp.gate_n = gp->n;

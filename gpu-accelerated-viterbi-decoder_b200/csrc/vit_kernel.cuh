@@ -80,6 +80,7 @@ struct KParams {
     unsigned gate_n;
     unsigned gate_super[8];
     unsigned long long gate_timeout_ns;   // a warp gives up on a gate after this long (vit_api.cu derives it from the copy size)
+    unsigned stage_out;                   // != 0: store decoded packs 8 slides (32 bytes per segment) at a time (output in a peer GPU's memory)
 };
 
 // ------------------------------------------------------------------------------------------------

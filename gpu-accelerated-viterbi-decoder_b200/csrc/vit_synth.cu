@@ -184,6 +184,51 @@ __global__ void count_errors_synth_kernel(SynthParams p, const void* __restrict_
     if ((threadIdx.x & 31) == 0 && errs) atomicAdd(total, errs);
 }
 
+// ---- depuncturing (the part that needs no new trellis): a punctured rate-k/n stream of soft symbols is
+// expanded to the rate-1/2 stream the decoder takes, with zero-valued symbols (erasures: they contribute 0 to every branch
+// metric) where the transmitter dropped one.  One thread = one 32-bit pack (or one symbol pair for FP32) of the OUTPUT.
+struct PunctParams {
+    unsigned period;          // stages per puncturing period
+    unsigned keep[2];         // bit t of keep[w]: symbol w (0: polynomial 0171, 1: 0133) of stage t of the period is transmitted
+    unsigned kept_per_period;
+    unsigned prefix[2][32];   // transmitted symbols of the period that precede (stage t, symbol w), in transmission order
+    int input_type;
+    unsigned long long n_out_syms, n_in_syms;
+};
+
+__device__ inline int32_t load_symbol(const void* in, int input_type, unsigned long long idx) {
+    switch (input_type) {
+        case 1: { uint32_t w = static_cast<const uint32_t*>(in)[idx >> 3]; int v = (int)((w >> (28 - 4 * (idx & 7))) & 0xF); return (v ^ 8) - 8; }
+        case 2: { uint32_t w = static_cast<const uint32_t*>(in)[idx >> 2]; return (int8_t)(w >> (24 - 8 * (idx & 3))); }
+        case 3: { uint32_t w = static_cast<const uint32_t*>(in)[idx >> 1]; return (int16_t)(w >> (16 - 16 * (idx & 1))); }
+        default: return 0;
+    }
+}
+
+__global__ void depuncture_kernel(PunctParams p, const void* __restrict__ in, uint32_t* __restrict__ out, unsigned long long n_words) {
+    const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const int per_word = p.input_type == 1 ? 8 : p.input_type == 2 ? 4 : 2;   // FP32: one symbol pair per thread
+    uint32_t word = 0;
+    float f[2] = {0.f, 0.f};
+    for (int j = 0; j < per_word; j++) {
+        const unsigned long long s = w * per_word + j;          // output symbol index
+        const unsigned long long stage = s >> 1;
+        const unsigned which = (unsigned)(s & 1), t = (unsigned)(stage % p.period);
+        bool have = s < p.n_out_syms && ((p.keep[which] >> t) & 1u);
+        const unsigned long long src = (stage / p.period) * p.kept_per_period + p.prefix[which][t];
+        have = have && src < p.n_in_syms;
+        if (p.input_type == 4) f[j] = have ? static_cast<const float*>(in)[src] : 0.f;
+        else {
+            const int32_t v = have ? load_symbol(in, p.input_type, src) : 0;
+            const int width = p.input_type == 1 ? 4 : p.input_type == 2 ? 8 : 16;
+            word = (word << width) | ((uint32_t)v & ((1u << width) - 1u));
+        }
+    }
+    if (p.input_type == 4) reinterpret_cast<float2*>(out)[w] = make_float2(f[0], f[1]);
+    else out[w] = word;
+}
+
 }  // namespace
 
 extern "C" {
@@ -264,6 +309,34 @@ int vit_count_errors_device(int options, const void* out_d, const void* bits_d, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(acc);
     return e == cudaSuccess ? VIT_OK : VIT_ERR_CUDA;
+}
+
+// Expand a punctured stream of soft symbols to the rate-1/2 stream the decoder takes.  keep0 / keep1: bit t set = the 0171 /
+// 0133 symbol of stage t of the period is transmitted (stage order, 0171 before 0133 inside a stage); e.g. rate 3/4:
+// period 3, keep0 = 0b101, keep1 = 0b011.  in_d: n_in_syms transmitted symbols packed like the decoder's input type (SOFT4,
+// SOFT8, SOFT16 or FP32 -- hard decisions have no erasure value); out_d receives n_out_stages * 2 symbols in the same
+// packing, zero where nothing was transmitted.
+int vit_depuncture_device(int input_type, const void* in_d, size_t n_in_syms, unsigned period, unsigned keep0, unsigned keep1,
+                          void* out_d, size_t n_out_stages, void* cuda_stream) {
+    if (input_type < 1 || input_type > 4 || !in_d || !out_d || period < 1 || period > 32) return VIT_ERR_ARG;
+    PunctParams p{};
+    p.period = period; p.keep[0] = keep0; p.keep[1] = keep1; p.input_type = input_type;
+    unsigned n = 0;
+    for (unsigned t = 0; t < period; t++)
+        for (unsigned w = 0; w < 2; w++) {
+            p.prefix[w][t] = n;
+            if ((p.keep[w] >> t) & 1u) n++;
+        }
+    if (n == 0) return VIT_ERR_ARG;
+    p.kept_per_period = n;
+    p.n_out_syms = 2ull * n_out_stages; p.n_in_syms = n_in_syms;
+    const unsigned per_word = input_type == 1 ? 8 : input_type == 2 ? 4 : 2;
+    const unsigned long long n_words = (p.n_out_syms + per_word - 1) / per_word;
+    if (n_words == 0) return VIT_OK;
+    const unsigned long long blocks = (n_words + 255) / 256;
+    if (blocks > 0x7fffffffull) return VIT_ERR_ARG;
+    depuncture_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(p, in_d, static_cast<uint32_t*>(out_d), n_words);
+    return cudaGetLastError() == cudaSuccess ? VIT_OK : VIT_ERR_CUDA;
 }
 
 // plain device-memory helpers so that host-only callers (no CUDA headers) can use the device-resident entry points

@@ -29,7 +29,7 @@ struct Args {
     int streams = 1;
     int gpus = 1;
     bool deviceSource = false;      // generate, decode and count errors on the device (no host pipeline)
-    std::string gather = "copy";    // how the stream job brings the packed output bits to GPU 0
+    std::string gather = "direct";  // how the stream job brings the packed output bits to GPU 0
     int wave = 8;                   // streams per decode launch
     int batch = 64;                 // streams generated ahead of each timed decode phase
 };
@@ -51,8 +51,8 @@ static void usage(const char* prog) {
               << "      --streams <integer>  Stream job: independent streams of -n bits, generated on the device,\n"
               << "                           sharded over --gpus in contiguous blocks, outputs gathered to GPU 0.\n"
               << "      --gpus <integer>     Number of GPUs (one decoder, one communicator and one host thread per GPU).\n"
-              << "      --gather <mode>      copy (copy engines over NVLink per finished wave, default) | nccl (ncclSend/ncclRecv) |\n"
-              << "                           direct (the kernel stores into GPU 0's buffer over NVLink) | none.\n"
+              << "      --gather <mode>      direct (the decode kernel stores into GPU 0's buffer over NVLink, default) |\n"
+              << "                           copy (copy engines per finished wave) | nccl (ncclSend/ncclRecv) | none.\n"
               << "      --wave <integer>     Streams per decode launch (default 8).\n"
               << "      --batch <integer>    Streams generated ahead of each timed decode phase (default 64).\n"
               << "      --device-source      Generate the channel, decode and count bit errors on the device\n"

@@ -149,6 +149,14 @@ int vit_synth_device_ex(int input_type, size_t n_bits, unsigned seed, int amp, d
 int vit_count_errors_synth_device(int options, const void* out_d, size_t messageLen, unsigned seed, int source,
                                   unsigned long long* errors, void* cuda_stream);
 
+/* Depuncturing pre-pass (new; the reference has no punctured modes): expands a punctured rate-k/n stream of soft symbols to
+ * the rate-1/2 stream vit_run_device takes, writing zero-valued symbols (erasures: 0 in every branch metric) where the
+ * transmitter dropped one.  keep0 / keep1: bit t set = the 0171 / 0133 symbol of stage t of the `period`-stage pattern is
+ * transmitted (e.g. DVB-S rate 3/4: period 3, keep0 = 0b101, keep1 = 0b011; 2/3: period 2, 0b01, 0b11).  Symbols are packed
+ * like the decoder's input type (SOFT4 / SOFT8 / SOFT16 / FP32; hard decisions have no erasure value). */
+int vit_depuncture_device(int input_type, const void* in_d, size_t n_in_syms, unsigned period, unsigned keep0, unsigned keep1,
+                          void* out_d, size_t n_out_stages, void* cuda_stream);
+
 /* Bit errors of a decoded stream counted on the device: #{ j < messageLen : out bit j != bits[j + 26] }
  * (the reference's BER loop, src/main.cpp:153-169); bits_d holds one byte per message bit.  Synchronous. */
 int vit_count_errors_device(int options, const void* out_d, const void* bits_d, size_t messageLen,

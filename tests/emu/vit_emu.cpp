@@ -112,6 +112,8 @@ void run_warp() {
 }
 }  // namespace
 
+static unsigned g_stage_out = 0;
+extern "C" void vit_emu_set_stage_out(int on) { g_stage_out = on ? 1u : 0u; }
 extern "C" void vit_emu_set_table(int tbl) { g_job.tbl = tbl == 32 ? 32 : 96; }
 extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 4 ? 4 : lanes == 16 ? 16 : 8; }
 
@@ -126,7 +128,7 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     g_job.kp.in = (const uint8_t*)in; g_job.kp.out = (uint8_t*)out;
     g_job.kp.in_stride = in_stride; g_job.kp.out_stride = out_stride;
     g_job.kp.in_bytes = in_bytes; g_job.kp.packs = M / bpp;
-    g_job.kp.segments = segments; g_job.kp.seg_first = 0; g_job.kp.seg_limit = segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u;
+    g_job.kp.segments = segments; g_job.kp.seg_first = 0; g_job.kp.seg_limit = segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u; g_job.kp.stage_out = g_stage_out;
     g_job.met = mt == 0 ? (((options >> 12) & 0xf) == 2 ? vitk::MET_B32D : vitk::MET_B32) : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
     g_job.in = it; g_job.bpp = bpp;
     g_job.smem = (uint8_t*)aligned_alloc(128, 64 * 1024);

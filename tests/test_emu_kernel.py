@@ -116,3 +116,20 @@ def test_dpx_tie_rule_differs_from_reg_only_for_int32(O):
     assert np.array_equal(O.decode(0x2011, packed, N), O.decode(0x0011, packed, N))          # int16x2: same table
     with pytest.raises(ValueError):
         O.decode(0x2021, packed, N)                                                          # no half2 DPX code
+
+
+@pytest.mark.parametrize("lanes", [8, 4, 16])
+@pytest.mark.parametrize("opt", [0x011, 0x112, 0x100, 0x004, 0x121])
+def test_kernel_source_staged_output_stores(emu, O, opt, lanes):
+    """KParams::stage_out (output buffer in a peer GPU's memory): packs are staged in shared memory and stored 8 slides at
+    a time; same words, for both pack widths (16-bit packs: aligned and unaligned segment starts, odd tails)."""
+    emu.vit_emu_set_stage_out(1)
+    emu.vit_emu_set_lanes(lanes)
+    try:
+        run_case(emu, O, opt, 3000 + 64 + 7, 12, seed=5, sigma=0.9)
+        run_case(emu, O, opt, 64 + 32 * 3 + 16, 8, seed=9, sigma=0.5)
+        run_case(emu, O, opt, 12000 + 64 + 16, 5, seed=11, sigma=1.0)          # > 8 slides per segment, ragged
+        run_case(emu, O, opt, 9000 + 64, 7, seed=12, sigma=0.3)
+    finally:
+        emu.vit_emu_set_stage_out(0)
+        emu.vit_emu_set_lanes(8)
