@@ -34,7 +34,7 @@ def test_depuncture_matches_numpy_twin_and_decodes(V, O, it, rate):
     amp = {1: 7, 2: 100, 3: 20000, 4: 6}[it]
     rng = np.random.default_rng(5)
     lo, hi = (-(1 << (WIDTH[it] - 1)), (1 << (WIDTH[it] - 1)) - 1) if it != 4 else (-8, 7)
-    sym = np.clip((2 * coded - 1) * amp + np.rint(rng.normal(0, amp * 0.25, coded.size)).astype(np.int64), lo, hi)
+    sym = np.clip((2 * coded - 1) * amp + np.rint(rng.normal(0, amp * 0.2, coded.size)).astype(np.int64), lo, hi)
     stage = np.arange(coded.size) // 2
     which = np.arange(coded.size) % 2
     keep = np.where(which == 0, (k0 >> (stage % period)) & 1, (k1 >> (stage % period)) & 1).astype(bool)
