@@ -153,7 +153,9 @@ int vit_count_errors_synth_device(int options, const void* out_d, size_t message
  * the rate-1/2 stream vit_run_device takes, writing zero-valued symbols (erasures: 0 in every branch metric) where the
  * transmitter dropped one.  keep0 / keep1: bit t set = the 0171 / 0133 symbol of stage t of the `period`-stage pattern is
  * transmitted (e.g. DVB-S rate 3/4: period 3, keep0 = 0b101, keep1 = 0b011; 2/3: period 2, 0b01, 0b11).  Symbols are packed
- * like the decoder's input type (SOFT4 / SOFT8 / SOFT16 / FP32; hard decisions have no erasure value). */
+ * like the decoder's input type (SOFT4 / SOFT8 / SOFT16 / FP32; hard decisions have no erasure value).  Note that the
+ * decoder keeps the reference's window constants (32-stage warm-up, 38-stage traceback merge), which are sized for the
+ * rate-1/2 code: rates above 2/3 decode with a truncation error floor. */
 int vit_depuncture_device(int input_type, const void* in_d, size_t n_in_syms, unsigned period, unsigned keep0, unsigned keep1,
                           void* out_d, size_t n_out_stages, void* cuda_stream);
 

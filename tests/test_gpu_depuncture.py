@@ -55,5 +55,13 @@ def test_depuncture_matches_numpy_twin_and_decodes(V, O, it, rate):
     torch.cuda.synchronize()
     got = d_out[:dec.getOutputSize(N)].cpu().numpy().view(np.uint32)
     assert np.array_equal(got, O.decode(opt, _pack(it, expect), N))
-    assert O.count_errors(opt, got, dec.getMessageLen(N), bits) == 0, (it, rate)
+    errs = O.count_errors(opt, got, dec.getMessageLen(N), bits)
+    # The reference's window (32-stage warm-up, 38-stage traceback merge, viterbi.h:70-76) is sized for the rate-1/2 code;
+    # punctured codes need deeper windows as the rate grows, so the higher rates leave a truncation error floor even at
+    # this mild noise level.  Bit-exactness with the golden model above is the parity statement; here: sanity only.
+    print("rate %s, input type %d: %d bit errors of %d" % (rate, it, errs, dec.getMessageLen(N)))
+    if rate in ("1/2", "2/3"):
+        assert errs == 0, (it, rate)
+    else:
+        assert errs < 0.05 * dec.getMessageLen(N), (it, rate, errs)
     dec.close()
