@@ -536,6 +536,9 @@ def main():
     step(0)
     drain(0)
     torch.cuda.synchronize()
+    if comm is not None and state["gather"] == V.GATHER_DIRECT:
+        # a sender's kernel must have recognised rank 0's buffer as remote (32-byte staged stores); rank 0 stores locally
+        assert dec.last_launch_staged_output() == (rank != 0), "direct-store gather: remote output buffer not recognised"
     gathering = comm is not None and state["gather"] != V.GATHER_NONE
     # rank 0 checks what arrived in the gathered buffer; a sender checks its local packs (or, with direct stores, its
     # block of rank 0's buffer through the mapping)

@@ -76,6 +76,7 @@ def lib():
         L.vit_kernel_info.restype = C.c_int
         L.vit_kernel_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4
         L.vit_launch_count.restype, L.vit_launch_count.argtypes = C.c_ulonglong, [vp]
+        L.vit_last_launch_staged_output.restype, L.vit_last_launch_staged_output.argtypes = C.c_int, [vp]
         L.vit_set_segments.restype, L.vit_set_segments.argtypes = C.c_int, [vp, C.c_uint]
         L.vit_last_error.restype, L.vit_last_error.argtypes = C.c_char_p, []
         L.vit_count_errors_device.restype = C.c_int
@@ -274,6 +275,9 @@ class ViterbiCUDA:
         v = [C.c_int(0) for _ in range(4)]
         _check(lib().vit_kernel_info(self.options, *[C.byref(x) for x in v]))
         return {"regs": v[0].value, "smem_bytes": v[1].value, "block_threads": v[2].value, "segs_per_block": v[3].value}
+
+    def last_launch_staged_output(self):
+        return bool(lib().vit_last_launch_staged_output(self._h))
 
     def launch_count(self):
         return int(lib().vit_launch_count(self._h))

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/vit_b200.h"
+#include "vit_internal.h"
 #include "vit_launch.h"
 
 namespace {
@@ -39,6 +40,28 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 }  // namespace
+namespace {
+struct RemoteRange { const char* base; size_t bytes; int owner; };
+std::mutex g_remote_mu;
+std::vector<RemoteRange> g_remote;
+}  // namespace
+void vit_note_remote_range(const void* base, size_t bytes, int owner_device) {
+    std::lock_guard<std::mutex> lk(g_remote_mu);
+    for (const auto& r : g_remote)
+        if (r.base == base) return;                      // several threads of one process register the same buffer
+    g_remote.push_back({static_cast<const char*>(base), bytes, owner_device});
+}
+void vit_forget_remote_range(const void* base) {
+    std::lock_guard<std::mutex> lk(g_remote_mu);
+    for (size_t i = 0; i < g_remote.size(); i++)
+        if (g_remote[i].base == base) { g_remote.erase(g_remote.begin() + (long)i); break; }
+}
+bool vit_in_remote_range(const void* p, int device) {
+    std::lock_guard<std::mutex> lk(g_remote_mu);
+    for (const auto& r : g_remote)
+        if (static_cast<const char*>(p) >= r.base && static_cast<const char*>(p) < r.base + r.bytes) return r.owner != device;
+    return false;
+}
 // shared with the other translation units of the library (vit_mg.cu); not exported
 int vit_set_error(int code, const char* msg) {
     snprintf(g_err, sizeof g_err, "%s", msg);
@@ -243,7 +266,7 @@ struct vit_handle {
     // decoded yet (its last 64..64+bitsPerPack-1 stages) wait here and are prepended to the next chunk
     void* carry_d = nullptr; size_t carry_cap = 0; size_t carry_syms = 0;
     unsigned long long stream_bits = 0;   // bits emitted since vit_stream_reset
-    const void* remote_checked = nullptr; bool remote_is = false;   // last output pointer examined for "lives on another GPU"
+    unsigned last_stage_out = 0;                                     // KParams::stage_out of the last launch
     bool force_stage_out = getenv("VIT_STAGE_OUT") != nullptr;       // measurement hook: staged output stores for local buffers too
     int upload_mode = VIT_UPLOAD_AUTO;    // vit_set_upload_mode
     unsigned long long gate_timeout_ns = 2000000000ull;
@@ -294,22 +317,20 @@ int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, 
     kp.one = 1u;
     kp.gate = h->gate_d; kp.gate_err = h->gate_err_d; kp.gate_epoch = h->epoch; kp.gate_n = 0;
     kp.gate_timeout_ns = h->gate_timeout_ns;
-    // output in another GPU's memory (a peer / IPC mapping: VIT_GATHER_DIRECT): the kernel stages 8 slides per store
+    // output in another GPU's memory (VIT_GATHER_DIRECT): the kernel stages 8 slides per store.  Mappings handed out by
+    // vit_comm_shared_alloc are registered (an IPC mapping looks like local memory to cudaPointerGetAttributes); any other
+    // peer pointer is recognised by its attributes.
     kp.stage_out = 0;
     if (out_d != h->out_d) {
-        if (out_d != h->remote_checked) {
+        bool remote = vit_in_remote_range(out_d, h->device);
+        if (!remote) {
             cudaPointerAttributes pa;
-            h->remote_is = cudaPointerGetAttributes(&pa, out_d) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->device;
+            remote = cudaPointerGetAttributes(&pa, out_d) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->device;
             cudaGetLastError();
-            h->remote_checked = out_d;
         }
-        kp.stage_out = (h->remote_is || h->force_stage_out) ? 1u : 0u;
+        kp.stage_out = (remote || h->force_stage_out) ? 1u : 0u;
     }
-    for (int i = 0; i < 8; i++) kp.gate_super[i] = 0;
-    if (gp && h->gate_d) {
-        kp.gate_n = gp->n;
-        for (unsigned i = 0; i < gp->n; i++) kp.gate_super[i] = gp->super[i];
-    }
+    h->last_stage_out = kp.stage_out;
     if (e0) VIT_CUDA(cudaEventRecord(e0, st));
     VIT_CUDA(h->kernel->launch(kp, st));
     h->launches++;
@@ -705,6 +726,7 @@ int vit_set_segments(vit_handle* h, unsigned segments) {
 }
 
 unsigned long long vit_launch_count(const vit_handle* h) { return h ? h->launches : 0; }
+int vit_last_launch_staged_output(const vit_handle* h) { return h ? (int)h->last_stage_out : 0; }
 
 int vit_run_device_batch(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, size_t nstreams,
                          size_t in_stride, size_t out_stride, void* cuda_stream, float* kernel_ms) {

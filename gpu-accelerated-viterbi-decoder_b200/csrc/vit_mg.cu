@@ -247,7 +247,7 @@ void vit_comm_destroy(vit_comm* c) {
     DevGuard g(c->device);
     for (auto& s : c->shared) {
         if (!s.ptr) continue;
-        if (s.mapped) cudaIpcCloseMemHandle(s.ptr);
+        if (s.mapped) { vit_forget_remote_range(s.ptr); cudaIpcCloseMemHandle(s.ptr); }
         else cudaFree(s.ptr);
     }
     if (c->gstream) cudaStreamDestroy(c->gstream);
@@ -350,11 +350,13 @@ int vit_comm_shared_alloc(vit_comm* c, void** ptr, size_t bytes, int root) {
     if (c->rank == root) { *ptr = mine; return VIT_OK; }
     if (c->single_process) {
         *ptr = (void*)(uintptr_t)msg.raw;                  // same address space; peer access was enabled at init
+        vit_note_remote_range(*ptr, bytes, c->peer_devices[root]);
         return VIT_OK;
     }
     void* mapped = nullptr;
     MG_CUDA(cudaIpcOpenMemHandle(&mapped, msg.h, cudaIpcMemLazyEnablePeerAccess));
     c->shared.push_back({mapped, true});
+    vit_note_remote_range(mapped, bytes, -1);
     *ptr = mapped;
     return VIT_OK;
 }

@@ -287,6 +287,9 @@ int main(int argc, char* argv[]) {
         return -1;
     }
     std::cout << "Pipeline executed." << std::endl;
+    if (a.deviceSource)
+        std::cout << "(device source: counter-hash bits, noise = sum of four uniforms (Irwin-Hall), truncated at +-3.46 sigma -- a\n"
+                     " bit-reproducible load generator; its BER is a decode check, not a BER-vs-SNR measurement)" << std::endl;
     std::cout << "Final results -> BEN: " << out.ben << "   BER: " << static_cast<double>(out.ben) / a.messageLen << std::endl;  // main.cpp:107-110
     std::cout << "Decoder -> kernel time: " << out.best_ms << " ms   decoded: " << out.decoded << " bits   "
               << out.decoded / (out.best_ms * 1e6) << " Gb/s";

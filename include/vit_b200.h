@@ -127,6 +127,10 @@ int vit_kernel_info(int options, int* regs, int* smem_bytes, int* block_threads,
 /* launches issued by this handle so far (one decode kernel per run) */
 unsigned long long vit_launch_count(const vit_handle* h);
 
+/* 1 if the last launch stored its packs 32 bytes per segment at a time (output buffer on another GPU: a mapping from
+ * vit_comm_shared_alloc or any peer pointer), 0 if one pack per slide (local output) */
+int vit_last_launch_staged_output(const vit_handle* h);
+
 /* test hook: number of stream segments (reference: 6400, viterbi.cu:19); 0 restores 6400 */
 int vit_set_segments(vit_handle* h, unsigned segments);
 
