@@ -248,7 +248,7 @@ void vit_comm_destroy(vit_comm* c) {
     for (auto& s : c->shared) {
         if (!s.ptr) continue;
         if (s.mapped) { vit_forget_remote_range(s.ptr); cudaIpcCloseMemHandle(s.ptr); }
-        else cudaFree(s.ptr);
+        else { vit_forget_remote_range(s.ptr); cudaFree(s.ptr); }
     }
     if (c->gstream) cudaStreamDestroy(c->gstream);
     if (c->ev_prod) cudaEventDestroy(c->ev_prod);
