@@ -182,11 +182,13 @@ private:
                 cv_.wait(lk, [this] { return stop_ || active_.load(); });
                 if (stop_) return;
             }
+            unsigned idle = 0;
             for (;;) {
                 const unsigned long long g = gen_.load(std::memory_order_acquire);
-                if (g != seen) { seen = g; drain(g); continue; }
+                if (g != seen) { seen = g; drain(g); idle = 0; continue; }
                 if (!active_.load(std::memory_order_acquire)) break;
                 for (int k = 0; k < 64 && gen_.load(std::memory_order_acquire) == seen; k++) spin_pause();
+                if (++idle > 4096) { std::this_thread::yield(); idle = 0; }     // be polite if the host is oversubscribed
             }
         }
     }
@@ -433,7 +435,12 @@ int ensure_staging(vit_handle* h, size_t in_bytes, size_t out_bytes) {
     }
     if (!h->pool) {
         const char* e = getenv("VIT_STAGE_THREADS");
-        int n = e ? atoi(e) : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        // default: up to 16 threads, and this process's share of the cores when several ranks share the host (torchrun and
+        // MPI launchers export the number of local ranks): the workers spin between blocks, oversubscription is ruinous
+        unsigned share = 1;
+        for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"})
+            if (const char* v = getenv(name)) { share = (unsigned)std::max(1, atoi(v)); break; }
+        int n = e ? atoi(e) : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency() / share));
         n = std::max(1, std::min(n, 64));
         h->pool = new (std::nothrow) StagePool(n - 1);
         if (!h->pool) return fail(VIT_ERR_ARG, "out of host memory");

@@ -62,7 +62,7 @@ int vit_run(vit_handle* h, const void* in_h, void* out_h, size_t inputNum, float
  *   AUTO        time-sliced upload (one decode launch that waits, inside the kernel, for column blocks of its input)
  *               when copies can run beside kernels, otherwise as CHUNKED.  Pinned buffers are read/written in place;
  *               pageable buffers (the reference's calling convention, viterbiDF.h:188-193) are staged through pinned
- *               buffers by worker threads (VIT_STAGE_THREADS, default min(16, cores); the caller is blocked meanwhile).  A run with kernel_ms != NULL
+ *               buffers by worker threads (VIT_STAGE_THREADS, default min(16, cores / local ranks); the caller is blocked meanwhile).  A run with kernel_ms != NULL
  *               always takes the SEQUENTIAL path, so that the reported time is the decode kernel alone.
  *   SEQUENTIAL  the reference's copy -> launch -> copy sequence (viterbi.cu:219-235).
  *   CHUNKED     segment-range pipeline: pinned buffers only, pageable buffers fall back to SEQUENTIAL.
