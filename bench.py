@@ -633,6 +633,13 @@ def main():
         dec.run(p_in[0], N, output_h=p_out)
         dec.run(h_in_np[0], N, output_h=h_out_np)
         e2e["pageable"]["equals_pinned_output"] = bool(np.array_equal(p_out, h_out_np))
+        # ... and both equal the device-resident decode of the same stream (the host-buffer paths overlap copies and kernel:
+        # a result that only matched itself would prove nothing)
+        chk = torch.zeros(out_stride1 + 256, dtype=torch.uint8, device=dev)
+        dec.run_device(streams[0].data_ptr(), chk.data_ptr(), N, stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        e2e["equals_device_decode"] = bool(np.array_equal(chk[:out_bytes].cpu().numpy(), h_out.numpy()))
+        assert e2e["equals_device_decode"] and e2e["pageable"]["equals_pinned_output"], "host-buffer decode differs from the device-resident decode"
 
     if rank == 0:
         hbm_peak, sm_max_mhz, peak_kind = measured_peaks()

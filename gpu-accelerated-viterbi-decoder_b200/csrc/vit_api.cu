@@ -333,6 +333,11 @@ int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, 
         kp.stage_out = (remote || h->force_stage_out) ? 1u : 0u;
     }
     h->last_stage_out = kp.stage_out;
+    for (int i = 0; i < 8; i++) kp.gate_super[i] = 0;
+    if (gp && h->gate_d) {
+        kp.gate_n = gp->n;
+        for (unsigned i = 0; i < gp->n; i++) kp.gate_super[i] = gp->super[i];
+    }
     if (e0) VIT_CUDA(cudaEventRecord(e0, st));
     VIT_CUDA(h->kernel->launch(kp, st));
     h->launches++;
