@@ -425,9 +425,7 @@ bool gated_upload_applies(const vit_handle* h, const HostRun& g) {
 
 int ensure_staging(vit_handle* h, size_t in_bytes, size_t out_bytes) {
     if (in_bytes > h->pin_in_cap) {
-        delete h->pool;
-    if (h->carry_d) cudaFree(h->carry_d);
-    if (h->pin_in) cudaFreeHost(h->pin_in);
+        if (h->pin_in) cudaFreeHost(h->pin_in);
         h->pin_in = nullptr; h->pin_in_cap = 0;
         VIT_CUDA(cudaHostAlloc(&h->pin_in, in_bytes + 256, cudaHostAllocDefault));
         h->pin_in_cap = in_bytes;
