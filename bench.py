@@ -1,26 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- decoded Gb/s of the B200-native Viterbi decoder on BASELINE.json's configuration.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--gather MODE]
 
-One "step" = one decode of one synthetic codeword stream (PRBS-free random bits -> K=7 0171/0133 encoder
--> BPSK + AWGN, sigma = 10^(-snr/5) -> x40000 -> saturating quantiser -> MSB-first packing, i.e. the
-reference harness's channel, reference src/main.cpp:131-138) through the hot path.  Default workload
-= BASELINE.json configs[1]: 32,000,000 message bits, 4-bit soft input, int16x2 core, 32-bit packs.
+One "step" = one decode of one synthetic codeword stream through the hot path.  The stream comes from the library's own
+device source (vit_synth_device_ex): PRBS-31 message bits -> K=7 0171/0133 encoder -> BPSK + noise, sd = 10^(-snr/5) ->
+x40000 -> saturating quantiser -> MSB-first packing, i.e. the reference harness's channel (reference src/main.cpp:131-138;
+at that scale every soft symbol saturates, as in ./main).  Default workload = BASELINE.json configs[1]: 32,000,000 message
+bits, 4-bit soft input, int16x2 core, 32-bit packs.
 
 Printed JSON (rank 0, one line):
-  value     whole-job decoded Gb/s with inputs resident in HBM, CUDA events on the launch stream,
-            max over ranks.  For N > 1 every rank decodes its own streams (weak scaling, no stream is
-            split) and the packed output bits are all-gathered over NCCL inside the timed region.
-  e2e       the same metric through the reference-facing call ViterbiCUDA.run(host_in, host_out)
-            (C ABI vit_run) with pinned HOST buffers: H2D copy, kernel, D2H copy every step.
-  roofline  the kernel is issue-bound, not HBM-bound: achieved decoded Gb/s against the
-            ACS-op issue roofline N_SM*4*f_SM / (3|6 warp-instructions per decoded bit); roofline_hbm is
-            the algorithmic-bytes view against MEASURED_PEAKS.json.
+  value     whole-job decoded Gb/s with inputs resident in HBM, CUDA events on the launch stream, max over ranks.  For
+            N > 1 every rank decodes its own streams (weak scaling, no stream is split) and the packed output bits reach
+            rank 0 inside the timed region: by default the decode kernel stores them straight into rank 0's buffer over
+            NVLink (--gather direct), alternatively through copy engines (copy) or NCCL send/recv (nccl) -- all three are
+            the library's own C code (vit_comm_gatherv, csrc/vit_mg.cu); value_without_gather is measured in the same run.
+  e2e       the same metric through the reference-facing call ViterbiCUDA.run(host_in, host_out) (C ABI vit_run): H2D
+            copy, kernel, D2H copy every step; e2e.value from pinned buffers, e2e.pageable from pageable numpy buffers (the
+            reference's calling convention); both outputs are checked against the device-resident decode.
+  roofline  the kernel is issue-bound, not HBM-bound: achieved decoded Gb/s against the ACS-op issue
+            roofline N_SM*4*f_SM / (3|6 warp-instructions per decoded bit); roofline_hbm is the algorithmic-bytes view
+            against MEASURED_PEAKS.json.
   cpu_baseline  the scalar C golden model (oracle/, "port") on the host cores, bounded sample.
-`--impl reference` times the reference's own CUDA decoder (oracle/_ref/libvitref.so, built from the
-unmodified reference sources for sm_100) through its own run(); if that library is absent it times the
-C golden model on the host cores instead.
+`--workload config5` runs BASELINE.json configs[4] (1024 x 256-Mbit s8 streams, strong scaling) through vit_job_run.
+`--impl reference` times the reference's own CUDA decoder (oracle/_ref/libvitref.so, built from the unmodified reference
+sources for sm_100) through its own run(); if that library is absent it times the C golden model on the host cores.
 """
 import argparse
 import importlib.util
