@@ -40,3 +40,14 @@ CASES = [
     # DPX flag: same core as REG in the reference (viterbi.cu:181,192,204)
     ("s4_b16_o32_dpx",   S4 | B16 | O32 | 0x1000, N_SMALL, 26, 0.90, False),
 ]
+
+# The reference's DPX code paths made live (oracle/_ref/libvitref_dpx.so): tests/golden/ref_vectors_dpx.npz
+DPX_CASES = [
+    ("dpx_s4_b32",       S4 | B32 | O32,   N_SMALL, 31,   0.90,  False),
+    ("dpx_h_b32_o16",    H | B32 | O16,    N_SMALL, 32,   0.80,  False),
+    ("dpx_s8_b16",       S8 | B16 | O32,   N_SMALL, 33,   0.90,  False),
+    ("dpx_tie_s4_b32",   S4 | B32 | O32,   N_SMALL, 1,    0.0,   True),     # differs from the REG code at phase 0
+    ("dpx_tie_s8_b32",   S8 | B32 | O16,   N_SMALL, 1,    0.0,   True),
+    ("dpx_tie_s4_b16",   S4 | B16 | O32,   N_SMALL, 1,    0.0,   True),     # int16x2: same table as REG
+    ("dpx_tie_f_b32",    F | B32 | O32,    N_SMALL, 1,    0.0,   True),
+]
