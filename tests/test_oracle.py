@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from vit_golden_cases import CASES
+from vit_golden_cases import CASES, DPX_CASES
 from vit_testlib import ALL_OPTS, GOLDEN
 
 
@@ -137,3 +137,27 @@ def test_oracle_matches_reference_golden_vectors(O, case):
     if ov.size and P // 6400 >= 3:
         got_ov = O.decode(opt, packed, N, flags=O.FLAG_REF_OVERRUN)
         assert np.all((ref[ov] == got[ov]) | (ref[ov] == got_ov[ov]))
+
+
+GOLDEN_DPX = os.path.join(os.path.dirname(GOLDEN), "ref_vectors_dpx.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN_DPX), reason="tests/golden/ref_vectors_dpx.npz not generated yet")
+@pytest.mark.parametrize("case", DPX_CASES, ids=[c[0] for c in DPX_CASES])
+def test_oracle_dpx_tie_table_matches_reference_dpx_vectors(O, emu, case):
+    """Pin of the VO_DPX_TIES table (CompMode value 2): the golden model -- and the product kernel source in the host
+    emulator -- reproduce what the reference's own DPX code paths produced on a B200 once compMode is forwarded to them
+    (oracle/ref_dpx_shim.cu, tests/golden/make_golden_dpx.py).  The stock reference never runs that code."""
+    from test_emu_kernel import emu_decode
+    name, opt, n, seed, sigma, zero = case
+    g = np.load(GOLDEN_DPX)
+    bits, packed, N = O.make_channel_det(n, opt & 0xF, seed=seed, sigma=sigma, zero=zero)
+    assert hashlib.sha256(packed.tobytes()).digest() == g[name + "/sha"].tobytes(), "input generator drifted"
+    ref = g[name + "/out"]
+    owned = np.ones(ref.size, bool)
+    owned[O.overrun_words(opt, N).astype(np.int64)] = False
+    got = O.decode(opt | O.DPX_TIES, packed, N)
+    assert np.array_equal(got[owned], ref[owned])
+    if (opt & 0xF0) == 0x00 and zero and (opt & 0xF) != 0:
+        assert not np.array_equal(O.decode(opt, packed, N)[owned], ref[owned])      # the REG tie rule differs (int32, phase 0)
+    assert np.array_equal(emu_decode(emu, O, opt | O.DPX_TIES, packed, N, 6400), got)
