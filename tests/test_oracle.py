@@ -161,3 +161,30 @@ def test_oracle_dpx_tie_table_matches_reference_dpx_vectors(O, emu, case):
     if (opt & 0xF0) == 0x00 and zero and (opt & 0xF) != 0:
         assert not np.array_equal(O.decode(opt, packed, N)[owned], ref[owned])      # the REG tie rule differs (int32, phase 0)
     assert np.array_equal(emu_decode(emu, O, opt | O.DPX_TIES, packed, N, 6400), got)
+
+
+@pytest.mark.parametrize("opt", [0x011, 0x100, 0x004, 0x112, 0x023])
+def test_chunked_restatement_emits_the_contiguous_message(O, opt):
+    """oracle.decode_chunked (the restatement of C ABI vit_stream_push): whatever the chunk sizes, the concatenated outputs
+    of a noiseless stream are the message bits 26, 27, ... without gap or repeat, and at most one pack per push short of
+    what a one-shot decode of the whole stream emits."""
+    it = opt & 0xF
+    spw = {0: 32, 1: 8, 2: 4, 3: 2, 4: 1}[it]
+    n_bits = 120_000
+    bits, packed, N = O.make_channel_det(n_bits, it, seed=3, sigma=0.0)
+    rng = np.random.default_rng(opt)
+    for lo, hi in ((1, 30), (200, 6000)):
+        chunks, left = [], N
+        while left >= spw:
+            c = min(int(rng.integers(lo, hi)) * spw, left // spw * spw)
+            chunks.append(c)
+            left -= c
+            if lo == 1 and sum(chunks) > 6000 * spw:
+                break
+        outs, pend = O.decode_chunked(opt, packed, chunks)
+        allw = np.concatenate(outs)
+        bpp = 16 if opt & 0x100 else 32
+        M = allw.size * bpp
+        assert O.count_errors(opt, allw, M, bits) == 0
+        assert 128 <= pend < 128 + 2 * bpp + 2 * spw or M == 0
+        assert M <= O.message_len(opt, sum(chunks)) and M >= O.message_len(opt, sum(chunks)) - bpp
