@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+# VIT_B200_LIB: another build of the same library (e.g. one compiled for other generator polynomials, csrc/vit_code.h)
+LIB_PATH = os.environ.get("VIT_B200_LIB") or os.path.join(_HERE, "libvitb200.so")
 
 # option bitfield, reference src/viterbi/viterbi.h:7-20
 HARD, SOFT4, SOFT8, SOFT16, FP32 = 0x0, 0x1, 0x2, 0x3, 0x4
@@ -58,7 +59,7 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ViterbiError("libvitb200.so is not built: run `make -C %s/csrc` (or __graft_entry__.build())" % _HERE)
+            raise ViterbiError("%s is not built: run `make -C %s/csrc` (or __graft_entry__.build())" % (LIB_PATH, _HERE))
         L = C.CDLL(LIB_PATH)
         sz, vp = C.c_size_t, C.c_void_p
         L.vit_create.restype, L.vit_create.argtypes = C.c_int, [C.POINTER(vp), C.c_int, C.c_int, sz]
@@ -71,6 +72,7 @@ def lib():
         for n in ("vit_input_size", "vit_message_len", "vit_output_size"):
             f = getattr(L, n)
             f.restype, f.argtypes = sz, [C.c_int, sz]
+        L.vit_code_parameters.restype, L.vit_code_parameters.argtypes = None, [C.POINTER(C.c_int)] * 3
         L.vit_options_valid.restype, L.vit_options_valid.argtypes = C.c_int, [C.c_int]
         L.vit_options_valid_ref.restype, L.vit_options_valid_ref.argtypes = C.c_int, [C.c_int]
         L.vit_kernel_info.restype = C.c_int
@@ -137,6 +139,13 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise ViterbiError("vit error %d: %s" % (rc, lib().vit_last_error().decode()))
+
+
+def code_parameters():
+    """(constLen, polyn1, polyn2) this build of the library decodes (vit_code_parameters; reference viterbi.h:61-63)."""
+    v = [C.c_int(0) for _ in range(3)]
+    lib().vit_code_parameters(*[C.byref(x) for x in v])
+    return tuple(x.value for x in v)
 
 
 def options_valid(options):

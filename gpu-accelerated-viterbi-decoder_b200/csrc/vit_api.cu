@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/vit_b200.h"
+#include "vit_code.h"
 #include "vit_internal.h"
 #include "vit_launch.h"
 
@@ -631,6 +632,13 @@ size_t vit_message_len(int o, size_t n) {
 }
 // reference viterbi.cu:90-92
 size_t vit_output_size(int o, size_t n) { return vit_message_len(o, n) / 8; }
+
+// reference viterbi.h:61-63 (constLen, polyn1, polyn2): the values this build was compiled for (vit_code.h)
+void vit_code_parameters(int* constLen, int* polyn1, int* polyn2) {
+    if (constLen) *constLen = VIT_CONST_LEN;
+    if (polyn1) *polyn1 = VIT_POLY1;
+    if (polyn2) *polyn2 = VIT_POLY2;
+}
 
 // reference viterbi.h:22-36
 int vit_options_valid_ref(int o) {

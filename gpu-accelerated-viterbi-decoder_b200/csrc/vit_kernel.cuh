@@ -2,7 +2,7 @@
 //
 // Replaces the reference's viterbi_core kernel and its three device headers
 // (reference src/viterbi/viterbi.cu:144-207, viterbiBM.cuh, viterbiACS.cuh, viterbiTB.cuh) with a
-// different mapping of the same algorithm (K=7, 64 states, polys 0171/0133, 6400 stream segments,
+// different mapping of the same algorithm (K=7, 64 states, polys 0171/0133 by default, 6400 stream segments,
 // 64-stage warm-up, register-exchange survivor words, 96-stage ring, traceback from state 0):
 //
 //   * 8 lanes per stream segment, 4 segments per warp (the reference: 32 lanes per segment).
@@ -39,6 +39,8 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <utility>
+
+#include "vit_code.h"
 
 #if defined(__CUDACC__)
 #include <cuda_fp16.h>
@@ -82,6 +84,10 @@ struct KParams {
     unsigned long long gate_timeout_ns;   // a warp gives up on a gate after this long (vit_api.cu derives it from the copy size)
     unsigned stage_out;                   // != 0: store decoded packs 8 slides (32 bytes per segment) at a time (output in a peer GPU's memory)
 };
+
+// code parameters of this build (vit_code.h): K = 7 is fixed, the generator polynomials default to the reference's
+constexpr int CONST_LEN = VIT_CONST_LEN;
+constexpr int POLY1 = VIT_POLY1, POLY2 = VIT_POLY2;
 
 // ------------------------------------------------------------------------------------------------
 // compile-time trellis geometry

@@ -8,7 +8,8 @@
 //   message bit i       = top bit of splitmix64(i + seed * 0xD1B54A32D192ED03)   (source 0), or
 //                         bit i of the PRBS-31 sequence x^31 + x^28 + 1 started from state `seed` (source 1: the
 //                         bench's message source; CPU twin vo_prbs31)
-//   coded symbols 2i,2i+1 = parities of the 7-bit buffer (bit 6 = newest) with 0171 / 0133   (viterbiDF.h:48-60)
+//   coded symbols 2i,2i+1 = parities of the 7-bit buffer (bit 6 = newest) with the generator polynomials
+//                         (vit_code.h; 0171 / 0133 as in the reference, viterbiDF.h:48-60)
 //   symbol value (Q8)   = +-(amp << 8) + ((u * sigma_q16) >> 16),  u = sum of the four 16-bit lanes of
 //                         splitmix64(j + seed * 0x100000001B3) - 2*65535   (~Gaussian, sd = 0.577 * sigma_q16 / 256)
 //   quantise            = floor(value / 256), then the reference's saturating quantiser and MSB-first packing
@@ -17,6 +18,7 @@
 #include <cstdint>
 
 #include "../../include/vit_b200.h"
+#include "vit_code.h"
 
 namespace {
 
@@ -132,7 +134,7 @@ __global__ void synth_kernel(SynthParams p, uint32_t* __restrict__ packed, uint8
             if (!live) u = 0;
             if (bits_out && live) bits_out[i] = (uint8_t)u;
             sr = (sr >> 1) | ((unsigned)u << 6);
-            const int c[2] = {__popc(sr & 0171) & 1, __popc(sr & 0133) & 1};
+            const int c[2] = {__popc(sr & VIT_POLY1) & 1, __popc(sr & VIT_POLY2) & 1};
             for (int k = 0; k < 2; k++) {
                 long long v = live ? symbol_value(p, 2ull * i + k, c[k]) : 0;
                 switch (p.input_type) {

@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "../../include/vit_b200.h"
+#include "../csrc/vit_code.h"   // VIT_CONST_LEN, VIT_POLY1, VIT_POLY2: the code parameters (defaults = the reference's)
 
 // ---- option bitfield: values are the contract (reference viterbi.h:7-20) ----------------------
 constexpr int CHANNEL_SHIFT = 0, METRIC_SHIFT = 4, DECODE_SHIFT = 8, COMP_SHIFT = 12;
@@ -75,9 +76,11 @@ struct ViterbiCUDA<options, false> {
     using decPack_t = std::conditional_t<outputType == O_B16, uint16_t, uint32_t>;
     using encPack_t = std::conditional_t<inputType == FP32, float, int32_t>;
 
-    static constexpr int constLen = 7;
-    static constexpr int polyn1 = 0171;
-    static constexpr int polyn2 = 0133;
+    // reference viterbi.h:61-63: 7, 0171, 0133.  A caller compiled with -DVIT_POLY1= / -DVIT_POLY2= must be linked with a
+    // library built with the same values (checked when a decoder is constructed).
+    static constexpr int constLen = VIT_CONST_LEN;
+    static constexpr int polyn1 = VIT_POLY1;
+    static constexpr int polyn2 = VIT_POLY2;
     static constexpr int roundup(int a, int b) { return a <= 0 ? 0 : (a + b - 1) / b * b; }
     static constexpr size_t roundup(size_t a, size_t b) { return a == 0 ? 0 : (a + b - 1) / b * b; }
     static constexpr int bitsPerMetric = metricType == M_B16 ? 16 : metricType == M_B32 ? 32 : 11;
@@ -106,8 +109,8 @@ public:
     using typename Base::metric_t;
 
     // reference viterbi.cu:23-36.  `device`: the reference always uses 0 (viterbi.cu:134).
-    ViterbiCUDA() { VIT_HANDLE_ERROR(vit_create(&h_, options, 0, 0)); }
-    explicit ViterbiCUDA(size_t inputNum, int device = 0) { VIT_HANDLE_ERROR(vit_create(&h_, options, device, inputNum)); }
+    ViterbiCUDA() { checkCode(); VIT_HANDLE_ERROR(vit_create(&h_, options, 0, 0)); }
+    explicit ViterbiCUDA(size_t inputNum, int device = 0) { checkCode(); VIT_HANDLE_ERROR(vit_create(&h_, options, device, inputNum)); }
     ~ViterbiCUDA() { vit_destroy(h_); }
     ViterbiCUDA(const ViterbiCUDA&) = delete;
     ViterbiCUDA& operator=(const ViterbiCUDA&) = delete;
@@ -140,5 +143,12 @@ public:
     size_t getOutputSize(size_t inputNum) { return vit_output_size(options, inputNum); }    // viterbi.cu:90-92
 
 private:
+    // the library decodes the code it was compiled for: it must be the one this header's constants describe
+    static void checkCode() {
+        int k = 0, p1 = 0, p2 = 0;
+        vit_code_parameters(&k, &p1, &p2);
+        if (k != Base::constLen || p1 != Base::polyn1 || p2 != Base::polyn2)
+            vit_detail::die("libvitb200 was built for other code parameters (constLen / polyn1 / polyn2) than this header", __FILE__, __LINE__);
+    }
     vit_handle* h_ = nullptr;
 };

@@ -113,6 +113,13 @@ size_t vit_input_size(int options, size_t inputNum);
 size_t vit_message_len(int options, size_t inputNum);
 size_t vit_output_size(int options, size_t inputNum);
 
+/* Code parameters this build of the library decodes (and its device source encodes): constraint length and the two
+ * generator polynomials, octal-style bit masks over the encoder register with bit 6 = newest bit -- the reference's
+ * ViterbiCUDA<>::constLen / polyn1 / polyn2 (viterbi.h:61-63: 7, 0171, 0133).  K = 7 is fixed; the polynomials are
+ * compile-time parameters of the library (csrc/vit_code.h, `make EXTRA="-DVIT_POLY1=0117 -DVIT_POLY2=0155" ...`) and
+ * must both tap bits 0 and 6, as the reference's own cores assume.  Any pointer may be NULL. */
+void vit_code_parameters(int* constLen, int* polyn1, int* polyn2);
+
 /* 1 if this library decodes the combination.  Superset of the reference's OptionsValid
  * (viterbi.h:22-36): FP16 metric with SOFT8/SOFT16 input is accepted (symbols are pre-scaled to
  * 5 bits); B16 metric with SOFT16 input is rejected as in the reference. */

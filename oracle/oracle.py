@@ -59,6 +59,8 @@ def lib():
         L.vo_count_errors.argtypes = [C.c_int, C.c_void_p, sz, C.c_void_p]
         L.vo_num_threads.restype = C.c_int
         L.vo_set_segments.restype, L.vo_set_segments.argtypes = None, [sz]
+        L.vo_set_polynomials.restype, L.vo_set_polynomials.argtypes = C.c_int, [C.c_uint, C.c_uint]
+        L.vo_get_polynomials.restype, L.vo_get_polynomials.argtypes = None, [C.POINTER(C.c_uint)] * 2
         _lib = L
     return _lib
 
@@ -185,6 +187,18 @@ def count_errors(options, out, message_len_, bits):
 def set_segments(w):
     """test hook: segment count used by decode/overrun_words (0 -> the reference's 6400)."""
     lib().vo_set_segments(w)
+
+
+def set_polynomials(polyn1=0, polyn2=0):
+    """test hook: generator polynomials of the decoder model and of encode() (0, 0 -> the reference's 0171, 0133)."""
+    if lib().vo_set_polynomials(polyn1, polyn2) != 0:
+        raise ValueError("polynomials must be 7-bit values tapping bits 0 and 6 (got 0%o, 0%o)" % (polyn1, polyn2))
+
+
+def get_polynomials():
+    a, b = C.c_uint(0), C.c_uint(0)
+    lib().vo_get_polynomials(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
 
 
 def num_threads():

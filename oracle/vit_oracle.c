@@ -4,7 +4,7 @@
  * Restates, state-indexed and without any lane/warp structure, what the reference's
  * viterbi_core kernel computes.  Citations are to /root/reference/src/viterbi/.
  *
- * Trellis (viterbi.h:61-63, viterbiDF.h:48-52): K=7, 64 states, rate 1/2, generators 0171/0133.
+ * Trellis (viterbi.h:61-63, viterbiDF.h:48-52): K=7, 64 states, rate 1/2, generators 0171/0133 (vo_set_polynomials: test hook).
  * The encoder buffer is (u<<6)|S with S the 6-bit state (newest bit at bit 5); next state
  * S' = (u<<5)|(S>>1); symbol k = (parity(buf&0171)<<1)|parity(buf&0133).  The two branches into a
  * state carry complementary symbols, so BM(odd predecessor) = -BM(even predecessor).
@@ -69,8 +69,21 @@ size_t vo_message_len(int o, size_t n) {
 /* viterbi.cu:90-92 */
 size_t vo_output_size(int o, size_t n) { return vo_message_len(o, n) / 8; }
 
+/* Generator polynomials (viterbi.h:62-63: polyn1 0171, polyn2 0133).  Test hook vo_set_polynomials: another K=7 code, for
+ * checking builds of the product library compiled for other polynomials (csrc/vit_code.h).  The restatement below, like the
+ * reference's cores, needs both polynomials to tap encoder bits 0 and 6 (complementary symbols on the two branches into a
+ * state); other values are rejected. */
+static unsigned g_poly1 = 0171, g_poly2 = 0133;
+int vo_set_polynomials(unsigned p1, unsigned p2) {
+    if (p1 == 0 && p2 == 0) { p1 = 0171; p2 = 0133; }
+    if (p1 > 0x7f || p2 > 0x7f || (p1 & 0101) != 0101 || (p2 & 0101) != 0101) return -1;
+    g_poly1 = p1; g_poly2 = p2;
+    return 0;
+}
+void vo_get_polynomials(unsigned* p1, unsigned* p2) { *p1 = g_poly1; *p2 = g_poly2; }
+
 static inline int parity7(unsigned v) { return __builtin_popcount(v & 0x7f) & 1; }
-static inline int sym_of(unsigned buf) { return (parity7(buf & 0171) << 1) | parity7(buf & 0133); }
+static inline int sym_of(unsigned buf) { return (parity7(buf & g_poly1) << 1) | parity7(buf & g_poly2); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* Branch metrics of one trellis stage.  `p` points at a zero-padded private copy of the       */
@@ -377,8 +390,8 @@ void vo_encode(const uint8_t* bits, size_t n, uint8_t* coded) {        /* viterb
     for (size_t i = 0; i < n; i++) {
         buffer >>= 1;
         buffer |= (unsigned)(bits[i] & 1) << 6;
-        coded[2 * i] = (uint8_t)parity7(buffer & 0171);
-        coded[2 * i + 1] = (uint8_t)parity7(buffer & 0133);
+        coded[2 * i] = (uint8_t)parity7(buffer & g_poly1);
+        coded[2 * i + 1] = (uint8_t)parity7(buffer & g_poly2);
     }
 }
 

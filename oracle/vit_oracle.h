@@ -85,7 +85,13 @@ size_t vo_overrun_words(int options, size_t inputNum, uint64_t* idx, size_t cap)
 
 /* ---- host pipeline twin (reference src/viterbiDF.h) -- input generation for tests ---- */
 
-/* K=7 (0171,0133) encoder, reference viterbiDF.h:36-63.  bits[n] in {0,1} -> coded[2n] in {0,1} */
+/* Test hook: the generator polynomials the decoder model and vo_encode use (default 0171, 0133 = reference viterbi.h:62-63;
+ * 0, 0 restores them).  Both must be 7-bit values tapping bits 0 and 6 (the reference's cores assume complementary branch
+ * symbols); returns -1 otherwise.  Process-wide. */
+int vo_set_polynomials(unsigned polyn1, unsigned polyn2);
+void vo_get_polynomials(unsigned* polyn1, unsigned* polyn2);
+
+/* K=7 encoder (polynomials as set above), reference viterbiDF.h:36-63.  bits[n] in {0,1} -> coded[2n] in {0,1} */
 void vo_encode(const uint8_t* bits, size_t n, uint8_t* coded);
 
 /* quantise+pack, reference viterbiDF.h:98-167: soft[nsym] floats (already noise-added, +-1 based),

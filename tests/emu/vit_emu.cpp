@@ -61,13 +61,16 @@ Job g_job;
 
 template <int MET, int IN, int BPP>
 void run_lane(int lane) {
+#if !defined(VIT_EMU_L8_ONLY)   // (builds for other code parameters instantiate the product geometry only: a third of the compile time)
     if (g_job.lanes == 16) {
         if (g_job.tbl == 32) vitk::l16::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
         else vitk::l16::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
     } else if (g_job.lanes == 4) {
         if (g_job.tbl == 32) vitk::l4::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
         else vitk::l4::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
-    } else {
+    } else
+#endif
+    {
         if (g_job.tbl == 32) vitk::l8::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
         else vitk::l8::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
     }
@@ -112,10 +115,17 @@ void run_warp() {
 }
 }  // namespace
 
+// the generator polynomials this emulator build was compiled for (-DVIT_POLY1= / -DVIT_POLY2=, csrc/vit_code.h)
+extern "C" void vit_emu_polynomials(int* p1, int* p2) { *p1 = vitk::POLY1; *p2 = vitk::POLY2; }
+
 static unsigned g_stage_out = 0;
 extern "C" void vit_emu_set_stage_out(int on) { g_stage_out = on ? 1u : 0u; }
 extern "C" void vit_emu_set_table(int tbl) { g_job.tbl = tbl == 32 ? 32 : 96; }
+#if defined(VIT_EMU_L8_ONLY)
+extern "C" void vit_emu_set_lanes(int) { g_job.lanes = 8; }
+#else
 extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 4 ? 4 : lanes == 16 ? 16 : 8; }
+#endif
 
 extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inputNum, unsigned segments,
                               unsigned nstreams, size_t in_stride, size_t out_stride) {

@@ -23,6 +23,30 @@ def load_pkg():
     return mod
 
 
+ALT_POLYS = (0o117, 0o155)
+ALT_LIB = os.path.join(PKG_DIR, "libvitb200_p%o_%o.so" % ALT_POLYS)
+
+
+def load_pkg_variant(lib_path, name):
+    """A second instance of the product package bound to another build of the library (VIT_B200_LIB is read when the
+    package is imported), e.g. one compiled for other generator polynomials."""
+    if name in sys.modules:
+        return sys.modules[name]
+    old = os.environ.get("VIT_B200_LIB")
+    os.environ["VIT_B200_LIB"] = lib_path
+    try:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(PKG_DIR, "__init__.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        if old is None:
+            del os.environ["VIT_B200_LIB"]
+        else:
+            os.environ["VIT_B200_LIB"] = old
+    return mod
+
+
 def has_gpu():
     try:
         import torch
