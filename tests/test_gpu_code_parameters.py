@@ -35,7 +35,7 @@ def test_variant_library_matches_golden_model(VA, alt_oracle, opt):
     dec = VA.ViterbiCUDA(opt)
     for n, kw in ((6400 * 32 * 3 + 64 + 32 * 77, dict(seed=31, sigma=0.9)),       # noisy, ragged
                   (6400 * 32 * 2 + 64, dict(seed=32, zero=True)),                 # every compare a tie
-                  (6400 * 32 * 40 + 64, dict(seed=33, sigma=0.3))):               # many super-steps per segment
+                  (6400 * 32 * 12 + 64, dict(seed=33, sigma=0.3))):               # several super-steps per segment
         bits, packed, N = O.make_channel_det(n, opt & 0xF, **kw)
         out = dec.run(packed, N, want_kernel_time=True)[0]
         assert np.array_equal(out, O.decode(opt, packed, N)), (hex(opt), n)
@@ -46,23 +46,29 @@ def test_variant_library_matches_golden_model(VA, alt_oracle, opt):
 
 def test_variant_library_device_source_and_round_trip(VA, alt_oracle):
     """the variant's device source encodes with ITS polynomials (bit-identical to the CPU twin under the same
-    polynomials) and its decoder returns the message; the default library does not decode that stream"""
-    import torch
+    polynomials) and its decoder returns the message"""
+    import ctypes as C
     O = alt_oracle
+    L = VA.lib()
     opt, n = 0x011, 6400 * 32 * 8 + 64
     N = 2 * n
     dec = VA.ViterbiCUDA(opt)
-    d_in = torch.zeros(dec.getInputSize(N) + 64, dtype=torch.uint8, device="cuda")
-    d_bits = torch.zeros(n, dtype=torch.uint8, device="cuda")
-    d_out = torch.zeros(dec.getOutputSize(N), dtype=torch.uint8, device="cuda")
-    VA.synth_device(opt & 0xF, n, d_in.data_ptr(), d_bits.data_ptr(), seed=7, amp=0, sigma=0.4)
-    torch.cuda.synchronize()
-    bits, packed, _ = O.make_channel_det(n, opt & 0xF, seed=7, sigma=0.4, bits_source="hash")
-    assert np.array_equal(d_bits.cpu().numpy(), bits)
-    assert np.array_equal(d_in[:dec.getInputSize(N)].cpu().numpy(), packed.view(np.uint8)[:dec.getInputSize(N)])
-    dec.run_device(d_in.data_ptr(), d_out.data_ptr(), N)
-    torch.cuda.synchronize()
-    M = dec.getMessageLen(N)
-    assert VA.count_errors_device(opt, d_out.data_ptr(), d_bits.data_ptr(), M) == 0
-    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), O.decode(opt, packed, N))
-    dec.close()
+    in_bytes, out_bytes = dec.getInputSize(N), dec.getOutputSize(N)
+    ptrs = [C.c_void_p() for _ in range(3)]
+    for p, nbytes in zip(ptrs, (in_bytes + 64, n, out_bytes)):
+        assert L.vit_dev_alloc(C.byref(p), nbytes) == 0
+    d_in, d_bits, d_out = [p.value for p in ptrs]
+    try:
+        VA.synth_device(opt & 0xF, n, d_in, d_bits, seed=7, amp=0, sigma=0.4)
+        assert L.vit_dev_sync() == 0
+        bits, packed, _ = O.make_channel_det(n, opt & 0xF, seed=7, sigma=0.4, bits_source="hash")
+        assert np.array_equal(VA.dev_to_host(d_bits, n), bits)
+        assert np.array_equal(VA.dev_to_host(d_in, in_bytes), packed.view(np.uint8)[:in_bytes])
+        dec.run_device(d_in, d_out, N)
+        assert L.vit_dev_sync() == 0
+        assert VA.count_errors_device(opt, d_out, d_bits, dec.getMessageLen(N)) == 0
+        assert np.array_equal(VA.dev_to_host(d_out, out_bytes).view(np.uint32), O.decode(opt, packed, N))
+    finally:
+        for p in ptrs:
+            L.vit_dev_free(p)
+        dec.close()
