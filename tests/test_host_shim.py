@@ -96,3 +96,37 @@ def test_harness_flags_without_gpu():
     assert bad.returncode == 1 and "Unknown or incomplete argument" in bad.stderr
     bad = subprocess.run([exe, "-i", "s16", "-m", "b16"], capture_output=True, text=True)
     assert bad.returncode != 0 and "16-bit metric does not support 16-bit soft decision input" in bad.stderr
+
+
+def test_shim_refuses_a_library_built_for_another_code(tmp_path):
+    """ViterbiCUDA<>::polyn1/polyn2 follow -DVIT_POLY1/-DVIT_POLY2 (csrc/vit_code.h), and constructing a decoder checks the
+    linked library's vit_code_parameters against them BEFORE any CUDA call: a caller compiled for the reference's code
+    refuses the (0117, 0155) library in the reference's print-and-exit style; compiled with the matching polynomials it
+    gets past the check (and then fails on the missing GPU, here)."""
+    from vit_testlib import ALT_LIB, ALT_POLYS
+    if not os.path.exists(ALT_LIB):
+        pytest.skip("variant library not built")
+    src = tmp_path / "code.cpp"
+    src.write_text('''
+#include "viterbi.h"
+int main() {
+    std::printf("%d %o %o\\n", ViterbiCUDA<0>::constLen, ViterbiCUDA<0>::polyn1, ViterbiCUDA<0>::polyn2);
+    std::fflush(stdout);
+    ViterbiCUDA<0> dec;
+    return 0;
+}
+''')
+    libname = os.path.basename(ALT_LIB)[3:-3]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")          # no device for either binary: only the check itself differs
+    for flags, constants, message in (([], "7 171 133", "built for other code parameters"),
+                                      (["-DVIT_POLY1=0%o" % ALT_POLYS[0], "-DVIT_POLY2=0%o" % ALT_POLYS[1]], "7 117 155", None)):
+        exe = tmp_path / ("code%d" % len(flags))
+        subprocess.check_call([GXX, "-std=c++17", "-Wall", "-I", HOST] + flags + ["-o", str(exe), str(src), "-L", PKG_DIR,
+                               "-l" + libname, "-Wl,-rpath," + PKG_DIR])
+        r = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+        assert r.stdout.strip() == constants
+        assert r.returncode == 1                              # EXIT_FAILURE either way on a machine without a GPU
+        if message:
+            assert message in r.stderr
+        else:
+            assert "built for other code parameters" not in r.stderr and " at line " in r.stderr
