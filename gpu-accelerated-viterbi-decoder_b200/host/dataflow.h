@@ -1,15 +1,18 @@
-// dataflow.h -- minimal synchronous dataflow runtime with the reference's interface
-// (reference src/dataflow/dataflow.h:1-133): ComputeElement / Pipeline / PipelineResult / operator|.
-// Re-authored; values move through the pipeline instead of being copied between elements.
+// dataflow.h -- the synchronous element/pipeline runtime behind the reference's dataflow interface
+// (reference src/dataflow/dataflow.h:12-133).  What a reference caller sees is kept: ComputeElement with process / probe /
+// status accessors, PipelineResult, Pipeline::add / run / printStatus, `a | b | c` chaining, the "Elapsed run time" status
+// and the text printStatus writes.  Behind that interface this is a different small runtime: a stage hands its value to the
+// next one by move (the reference copies the std::any between elements, and again into the result), the timing and the
+// duration formatting live in helpers of their own, and every element can describe itself to a stream.
 #pragma once
 
 #include <any>
 #include <chrono>
-#include <iomanip>
+#include <cstdio>
 #include <iostream>
 #include <map>
 #include <optional>
-#include <sstream>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <typeinfo>
@@ -18,78 +21,108 @@
 
 using OptData = std::optional<std::any>;
 
+namespace dataflow_detail {
+
+// "12 us" / "3.46 ms" / "1.20 s": the three ranges of the reference's status line (dataflow.h:54-66)
+inline std::string human_time(long long microseconds) {
+    char text[48];
+    if (microseconds > 1000000) std::snprintf(text, sizeof text, "%.2f s", (double)microseconds / 1e6);
+    else if (microseconds > 1000) std::snprintf(text, sizeof text, "%.2f ms", (double)microseconds / 1e3);
+    else std::snprintf(text, sizeof text, "%lld us", microseconds);
+    return text;
+}
+
+// wall time of one stage, in the unit the status map stores
+class Stopwatch {
+public:
+    Stopwatch() : begin_(clock::now()) {}
+    std::chrono::microseconds lap() const { return std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - begin_); }
+
+private:
+    using clock = std::chrono::high_resolution_clock;
+    clock::time_point begin_;
+};
+
+inline const char* const kElapsedKey = "Elapsed run time";
+
+}  // namespace dataflow_detail
+
+// One processing stage.  A source ignores its (empty) input and produces data; every other stage transforms the value
+// it is given.  Subclasses publish measurements through the status map and say how to print them.
 class ComputeElement {
 public:
     virtual ~ComputeElement() = default;
 
-    // in == nullopt: the element is a source and makes its own data
-    virtual std::any process(const OptData& in) = 0;
+    virtual std::any process(const OptData& in) = 0;                                   // reference dataflow.h:27
+    virtual std::string getStatusString(const std::string& /*key*/) const { return "(Not printable)"; }
 
-    ComputeElement& probe() { probed_ = true; return *this; }
-    bool isProbed() const { return probed_; }
+    // keep this stage's output in PipelineResult::probed_outputs
+    ComputeElement& probe() { keep_output_ = true; return *this; }
+    bool isProbed() const { return keep_output_; }
 
-    void setStatus(const std::string& key, std::any value) { status[key] = std::move(value); }
-    std::any getStatus(const std::string& key) const { return status.at(key); }
+    // status map: name -> value of any type (the runtime itself files the stage's wall time under "Elapsed run time")
+    void setStatus(const std::string& key, std::any value) { status.insert_or_assign(key, std::move(value)); }
+    std::any getStatus(const std::string& key) const { return status.at(key); }       // throws std::out_of_range
     const std::map<std::string, std::any>& getStatusMap() const { return status; }
-
-    virtual std::string getStatusString(const std::string&) const { return "(Not printable)"; }
-
     std::string getStatusStringAll(const std::string& key) const {
-        if (key != "Elapsed run time") return getStatusString(key);
-        const auto us = std::any_cast<std::chrono::microseconds>(getStatus(key)).count();
-        std::ostringstream os;
-        if (us > 1000000) os << std::fixed << std::setprecision(2) << us / 1e6 << " s";
-        else if (us > 1000) os << std::fixed << std::setprecision(2) << us / 1e3 << " ms";
-        else os << us << " us";
-        return os.str();
+        if (key == dataflow_detail::kElapsedKey)
+            return dataflow_detail::human_time(std::any_cast<std::chrono::microseconds>(status.at(key)).count());
+        return getStatusString(key);
+    }
+
+    // the block printStatus shows for this stage
+    void describe(std::ostream& os, int position) const {
+        os << "Element " << position << " (type: " << typeid(*this).name() << "):\n";
+        if (status.empty()) os << "  - No status information.\n";
+        for (const auto& entry : status) os << "  - " << entry.first << ": " << getStatusStringAll(entry.first) << "\n";
     }
 
 protected:
     std::map<std::string, std::any> status;
 
 private:
-    bool probed_ = false;
+    bool keep_output_ = false;
 };
 
 struct PipelineResult {
     std::any final_output;
-    std::vector<std::any> probed_outputs;
+    std::vector<std::any> probed_outputs;      // one per probed stage, in pipeline order
 };
 
+// An ordered chain of stages owned by the caller (the pipeline stores pointers, as the reference's does).
 class Pipeline {
 public:
-    Pipeline& add(ComputeElement& e) { stages_.push_back(&e); return *this; }
+    Pipeline& add(ComputeElement& stage) { chain_.push_back(&stage); return *this; }
 
     PipelineResult run() {
-        PipelineResult res;
-        OptData cur;
-        for (ComputeElement* e : stages_) {
-            const auto t0 = std::chrono::high_resolution_clock::now();
-            cur = e->process(cur);
-            const auto t1 = std::chrono::high_resolution_clock::now();
-            e->setStatus("Elapsed run time", std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0));
-            if (e->isProbed()) res.probed_outputs.push_back(*cur);
+        PipelineResult result;
+        OptData value;                          // empty: the first stage is a source
+        for (ComputeElement* stage : chain_) {
+            const dataflow_detail::Stopwatch watch;
+            std::any produced = stage->process(value);
+            stage->setStatus(dataflow_detail::kElapsedKey, watch.lap());
+            if (stage->isProbed()) result.probed_outputs.push_back(produced);          // a probe is the only copy made
+            value.emplace(std::move(produced));
         }
-        if (!cur.has_value()) throw std::runtime_error("Pipeline produced no output");
-        res.final_output = std::move(*cur);
-        return res;
+        if (!value) throw std::runtime_error("Pipeline produced no output");
+        result.final_output = std::move(*value);
+        return result;
     }
 
     void printStatus() const {
         std::cout << "--- Pipeline Status ---\n";
-        int idx = 0;
-        for (const ComputeElement* e : stages_) {
-            std::cout << "Element " << idx++ << " (type: " << typeid(*e).name() << "):\n";
-            if (e->getStatusMap().empty()) std::cout << "  - No status information.\n";
-            for (const auto& kv : e->getStatusMap())
-                std::cout << "  - " << kv.first << ": " << e->getStatusStringAll(kv.first) << "\n";
-        }
+        for (size_t i = 0; i < chain_.size(); i++) chain_[i]->describe(std::cout, (int)i);
         std::cout << "--- End of Status ---\n";
     }
 
 private:
-    std::vector<ComputeElement*> stages_;
+    std::vector<ComputeElement*> chain_;
 };
 
-inline Pipeline operator|(ComputeElement& a, ComputeElement& b) { Pipeline p; p.add(a).add(b); return p; }
-inline Pipeline operator|(Pipeline p, ComputeElement& b) { p.add(b); return p; }
+// `source | encoder | channel | decoder`
+inline Pipeline operator|(ComputeElement& first, ComputeElement& second) {
+    Pipeline p;
+    p.add(first).add(second);
+    return p;
+}
+inline Pipeline operator|(Pipeline chain, ComputeElement& next) { return std::move(chain.add(next)); }
