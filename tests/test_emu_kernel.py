@@ -133,3 +133,36 @@ def test_kernel_source_staged_output_stores(emu, O, opt, lanes):
     finally:
         emu.vit_emu_set_stage_out(0)
         emu.vit_emu_set_lanes(8)
+
+
+@pytest.mark.parametrize("opt", [0x012, 0x111, 0x004])
+def test_kernel_source_multi_stream_strides(emu, O, opt):
+    """Several independent streams per launch (grid.y = stream; BASELINE configs[4] shape): stream s is read at
+    in + s * in_stride and decoded to out + s * out_stride, nothing is written between or after the streams."""
+    W, ns, n = 9, 3, 2000 + 64 + 5
+    streams = [O.make_channel_det(n, opt & 0xF, seed=40 + s, sigma=0.8) for s in range(ns)]
+    N = streams[0][2]
+    in_bytes, out_bytes = O.input_size(opt, N), O.output_size(opt, N)
+    in_stride, out_stride = (in_bytes + 4 + 255) // 256 * 256, (out_bytes + 255) // 256 * 256
+    buf = np.zeros(ns * in_stride + 64, np.uint8)
+    off = (-buf.ctypes.data) % 16
+    for s, (_, packed, _) in enumerate(streams):
+        buf[off + s * in_stride: off + s * in_stride + in_bytes] = packed.view(np.uint8)[:in_bytes]
+    out = np.full(ns * out_stride + 16, 0xEE, np.uint8)
+    O.set_segments(W)
+    try:
+        refs = [O.decode(opt, packed, N) for _, packed, _ in streams]
+    finally:
+        O.set_segments(0)
+    for tbl in (96, 32):
+        emu.vit_emu_set_table(tbl)
+        try:
+            out[:] = 0xEE
+            assert emu.vit_emu_decode(opt, buf[off:].ctypes.data, out.ctypes.data, N, W, ns, in_stride, out_stride) == 0
+        finally:
+            emu.vit_emu_set_table(96)
+        for s in range(ns):
+            got = out[s * out_stride: s * out_stride + out_bytes].view(O.out_dtype(opt))
+            assert np.array_equal(got, refs[s]), (tbl, s)
+            assert np.all(out[s * out_stride + out_bytes: (s + 1) * out_stride] == 0xEE), (tbl, s)
+        assert np.all(out[ns * out_stride:] == 0xEE)
