@@ -22,6 +22,7 @@ Printed JSON (rank 0, one line):
             roofline N_SM*4*f_SM / (3|6 warp-instructions per decoded bit); roofline_hbm is the algorithmic-bytes view
             against MEASURED_PEAKS.json.
   cpu_baseline  the scalar C golden model (oracle/, "port") on the host cores, bounded sample.
+  reference_cuda  the reference's own CUDA decoder (oracle/_ref, built for sm_100) timed in the same run on the same GPU (N = 1).
 `--workload config5` runs BASELINE.json configs[4] (1024 x 256-Mbit s8 streams, strong scaling) through vit_job_run.
 `--impl reference` times the reference's own CUDA decoder (oracle/_ref/libvitref.so, built from the unmodified reference
 sources for sm_100) through its own run(); if that library is absent it times the C golden model on the host cores.
@@ -247,6 +248,29 @@ def cpu_baseline(options, n_bits, snr, budget_s=12.0):
             break
     return {"value": M * reps / dt / 1e9, "unit": "Gb/s", "cores": O.num_threads(), "kind": "port",
             "sample": "%d x full decode of a %d-bit stream (same options), OpenMP over the 6400 segments" % (reps, n_cpu)}
+
+
+def reference_cuda_baseline(options, n_bits, snr, reps=10):
+    """The reference's own CUDA decoder (oracle/_ref/libvitref.so, the unmodified sources built for sm_100) timed in THIS run
+    on the same GPU, beside the CPU baseline: its own cudaEvent kernel time (viterbi.cu:224-232) on a stream of the same
+    options.  A reported baseline for the line (BASELINE.json: "three baselines timed on the same box in the same run");
+    the driver's ratio comes from the separate `--impl reference` arm.  Never raises: a failure is reported in the dict."""
+    try:
+        from oracle import oracle as O
+        if O.ref_lib() is None or O.ref_lib().ref_device_count() <= 0:
+            return {"unavailable": "oracle/_ref/libvitref.so not built or no device"}
+        if not O.lib().vo_options_valid_ref(options):
+            return {"unavailable": "the reference rejects this option combination (viterbi.h:22-36)"}
+        n_ref = min(n_bits, 32_000_000)
+        bits, packed, N = O.make_channel(n_ref, options & 0xF, snr_db=snr, seed=5, prbs=True)
+        M = O.message_len(options, N)
+        for _ in range(3):
+            O.ref_decode(options, packed, N)
+        kms = [O.ref_decode(options, packed, N)[1] for _ in range(reps)]
+        return {"value": M / (statistics.mean(kms) * 1e6), "unit": "Gb/s", "kernel_ms": statistics.mean(kms), "kind": "reference CUDA decoder, -arch=sm_100",
+                "sample": "%d x ViterbiCUDA::run on a %d-bit stream (same options), its own cudaEvent kernel time" % (reps, n_ref)}
+    except Exception as e:          # a baseline must never cost the line
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
 
 def run_reference(args, options, n_bits, snr):
@@ -684,6 +708,7 @@ def main():
                               "value_by_wall_clock": M * S * world * args.steps / (ms_wall_max * 1e6)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(options, n_bits, snr)
+            line["reference_cuda"] = reference_cuda_baseline(options, n_bits, snr)
         print(json.dumps(line))
     dec.close()
     if comm is not None:

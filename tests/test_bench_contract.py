@@ -71,3 +71,19 @@ def test_clock_summary_flags_throttle_reasons():
     assert s["sm_mhz"] == 1965.0 and s["sm_max_mhz"] == 1965.0           # median of the samples INSIDE the timed region
     assert s["samples_in_timed_region"] == 3 and s["samples_under_load"] == 5
     assert s["reasons"] == ["sw_power_cap"]
+
+
+def test_same_run_reference_baseline_never_raises():
+    """bench.py's `reference_cuda` entry (the reference's CUDA decoder timed in the same run): without a device it reports
+    why it is unavailable instead of costing the line"""
+    B = _bench()
+    old = os.environ.get("CUDA_VISIBLE_DEVICES")
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        r = B.reference_cuda_baseline(0x011, 32_000_000, 15.0)
+    finally:
+        if old is None:
+            del os.environ["CUDA_VISIBLE_DEVICES"]
+        else:
+            os.environ["CUDA_VISIBLE_DEVICES"] = old
+    assert "unavailable" in r or r["value"] > 0
