@@ -95,6 +95,7 @@ constexpr int POLY1 = VIT_POLY1, POLY2 = VIT_POLY2;
 constexpr int mod6(int x) { return ((x % 6) + 6) % 6; }
 constexpr int SUPER = 96;       // unroll period
 constexpr int par3(int v) { return ((v >> 0) ^ (v >> 1) ^ (v >> 2) ^ (v >> 3)) & 1; }   // parity of up to 4 bits
+constexpr int par6(int v) { return (v ^ (v >> 1) ^ (v >> 2) ^ (v >> 3) ^ (v >> 4) ^ (v >> 5)) & 1; }   // ... of up to 6 (compile-time uses)
 
 template <int IN> struct InTraits;
 template <> struct InTraits<IN_HARD> { static constexpr int B96 = 24; };
@@ -577,6 +578,15 @@ namespace l4 {
 namespace l16 {
 #include "vit_kernel_map.inc"
 }  // namespace l16
+#undef VIT_NLB
+// vitk::l1  ONE lane per segment, 32 segments per warp, 64 states per lane: no exchanges and no operand table at all, ~30 %
+//           fewer instructions per decoded bit, but only 200 warps per stream -- the geometry for launches of many streams
+//           (vit_kernel_l1.inc; the map algebra with no lane bits is the same code).
+#define VIT_NLB 0
+namespace l1 {
+#include "vit_kernel_map.inc"
+#include "vit_kernel_l1.inc"
+}  // namespace l1
 #undef VIT_NLB
 
 }  // namespace vitk

@@ -62,7 +62,9 @@ Job g_job;
 template <int MET, int IN, int BPP>
 void run_lane(int lane) {
 #if !defined(VIT_EMU_L8_ONLY)   // (builds for other code parameters instantiate the product geometry only: a third of the compile time)
-    if (g_job.lanes == 16) {
+    if (g_job.lanes == 1) {
+        vitk::l1::warp_body_l1<MET, IN, BPP>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
+    } else if (g_job.lanes == 16) {
         if (g_job.tbl == 32) vitk::l16::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
         else vitk::l16::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
     } else if (g_job.lanes == 4) {
@@ -124,7 +126,7 @@ extern "C" void vit_emu_set_table(int tbl) { g_job.tbl = tbl == 32 ? 32 : 96; }
 #if defined(VIT_EMU_L8_ONLY)
 extern "C" void vit_emu_set_lanes(int) { g_job.lanes = 8; }
 #else
-extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 4 ? 4 : lanes == 16 ? 16 : 8; }
+extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 4 ? 4 : lanes == 16 ? 16 : lanes == 1 ? 1 : 8; }
 #endif
 
 extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inputNum, unsigned segments,

@@ -86,3 +86,26 @@ def test_no_cpu_fallback_in_product_sources():
                 for needle in ("vit_oracle.h", "libvitoracle", "libvitref", "from oracle", "import oracle", "oracle/",
                                "vo_decode", "libvitemu", "vit_emu"):
                     assert needle not in txt, (dirpath, f, needle)
+
+
+def test_one_lane_per_segment_geometry_cross_compiles(tmp_path):
+    """csrc/vit_kernel_l1.inc (the many-stream geometry the library does not instantiate yet) builds for sm_100a: no
+    spills for the packed cores, and its trellis stages contain no shuffle at all."""
+    import shutil
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on this machine")
+    obj = tmp_path / "l1_probe.o"
+    r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+                        "-I", os.path.join(PKG_DIR, "csrc"), "-c", os.path.join(ROOT, "scripts", "l1_probe.cu"), "-o", str(obj)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    blocks = re.split(r"Compiling entry function '", r.stderr)[1:]
+    assert len(blocks) == 6
+    for b in blocks:
+        name = b.split("'")[0]
+        regs = int(re.search(r"Used (\d+) registers", b).group(1))
+        assert regs <= 200, (name, regs)
+        if "ILi1E" in name or "ILi2E" in name:                       # int16x2 and half2 cores
+            assert "0 bytes spill stores" in b, name
+    sass = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
+    assert "SHFL" not in sass and "LDGSTS" in sass and "VIMNMX" in sass

@@ -1,6 +1,6 @@
 """CPU fuzz of the product kernel SOURCE (host emulator, tests/emu) against the golden model: random option values,
 stream lengths from below one pack to dozens of packs per segment, random segment counts, noise from none to heavy,
-saturated and all-tie inputs, both operand-table builds, all three lane geometries, staged and direct output stores.
+saturated and all-tie inputs, both operand-table builds, all four lane geometries (8 = the product's, 4, 16, and one lane per segment), staged and direct output stores.
 Fixed seed, bounded time.  (The same comparison on the sm_100a binary: scripts/parity_fuzz.py inside the -m gpu suite.)"""
 import time
 
@@ -15,7 +15,7 @@ OPTS = ALL_OPTS + [0x2000 | o for o in ALL_OPTS if (o & 0xF0) != 0x20]      # + 
 
 def test_kernel_source_fuzz(emu, O):
     rng = np.random.default_rng(20261018)
-    t0, cases, by_geom = time.perf_counter(), 0, {8: 0, 4: 0, 16: 0}
+    t0, cases, by_geom = time.perf_counter(), 0, {8: 0, 4: 0, 16: 0, 1: 0}
     try:
         while time.perf_counter() - t0 < BUDGET_S:
             opt = int(OPTS[rng.integers(len(OPTS))])
@@ -33,7 +33,7 @@ def test_kernel_source_fuzz(emu, O):
                 kw["sigma"] = float(rng.choice([0.0, 0.3, 0.8, 1.5, 3.0]))
             zero = kw.pop("zero", False)
             bits, packed, N = O.make_channel_det(max(n, 64), it, zero=zero, **kw)
-            lanes = int(rng.choice([8, 8, 4, 16]))
+            lanes = int(rng.choice([8, 8, 4, 16, 1]))
             tbl = int(rng.choice([96, 32]))
             staged = int(rng.random() < 0.3)
             emu.vit_emu_set_lanes(lanes); emu.vit_emu_set_table(tbl); emu.vit_emu_set_stage_out(staged)

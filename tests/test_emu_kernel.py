@@ -140,6 +140,18 @@ def test_kernel_source_multi_stream_strides(emu, O, opt):
     """Several independent streams per launch (grid.y = stream; BASELINE configs[4] shape): stream s is read at
     in + s * in_stride and decoded to out + s * out_stride, nothing is written between or after the streams."""
     W, ns, n = 9, 3, 2000 + 64 + 5
+    _multi_stream_case(emu, O, opt, W, ns, n, (96, 32))
+
+
+def test_kernel_source_multi_stream_strides_one_lane_geometry(emu, O):
+    emu.vit_emu_set_lanes(1)
+    try:
+        _multi_stream_case(emu, O, 0x012, 41, 3, 41 * 32 * 9 + 64 + 5, (96,))
+    finally:
+        emu.vit_emu_set_lanes(8)
+
+
+def _multi_stream_case(emu, O, opt, W, ns, n, tbls):
     streams = [O.make_channel_det(n, opt & 0xF, seed=40 + s, sigma=0.8) for s in range(ns)]
     N = streams[0][2]
     in_bytes, out_bytes = O.input_size(opt, N), O.output_size(opt, N)
@@ -154,7 +166,7 @@ def test_kernel_source_multi_stream_strides(emu, O, opt):
         refs = [O.decode(opt, packed, N) for _, packed, _ in streams]
     finally:
         O.set_segments(0)
-    for tbl in (96, 32):
+    for tbl in tbls:
         emu.vit_emu_set_table(tbl)
         try:
             out[:] = 0xEE
@@ -166,3 +178,21 @@ def test_kernel_source_multi_stream_strides(emu, O, opt):
             assert np.array_equal(got, refs[s]), (tbl, s)
             assert np.all(out[s * out_stride + out_bytes: (s + 1) * out_stride] == 0xEE), (tbl, s)
         assert np.all(out[ns * out_stride:] == 0xEE)
+
+
+@pytest.mark.parametrize("opt", ALL_OPTS + [0x2001, 0x2104, 0x2011])
+def test_kernel_source_one_lane_per_segment_geometry(emu, O, opt):
+    """vitk::l1 (csrc/vit_kernel_l1.inc): one lane per segment, 32 segments per warp, all 64 states of a segment in one
+    thread's registers -- no exchanges, no operand table, a one-slot ring, ping-pong register sets.  The many-stream
+    geometry identified as the next step; same output words as the golden model for every option value:
+    noisy, all-tie, short, long saturated segments, several warps with a partly filled last one, several streams."""
+    emu.vit_emu_set_lanes(1)
+    try:
+        run_case(emu, O, opt, 3000 + 64 + 7, 12, seed=5, sigma=0.9)
+        run_case(emu, O, opt, 1500 + 64, 5, seed=1, zero=True)
+        run_case(emu, O, opt, 64 + 32 * 3 + 16, 8, seed=9, sigma=0.5)
+        amp = {0: 64, 1: 7, 2: 127, 3: 32767, 4: 128}[opt & 0xF]
+        run_case(emu, O, opt, 12000 + 64, 4, seed=11, sigma=1.0, amp=amp)
+        run_case(emu, O, opt, 40 * 32 * 70 + 64 + 5, 70, seed=3, sigma=0.8)
+    finally:
+        emu.vit_emu_set_lanes(8)
