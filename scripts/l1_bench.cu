@@ -1,5 +1,5 @@
-// l1_bench.cu -- the measurement the one-lane-per-segment geometry (csrc/vit_kernel_l1.inc) still needs: NOT RUN YET (the
-// round's GPU budget was spent when the geometry was written; it is bit-exact in the host emulator and cross-compiles).
+// l1_bench.cu -- measurement harness of the one-lane-per-segment geometry (csrc/vit_kernel_l1.inc), which the library does not
+// instantiate yet.  Result of its one run on a B200: profiles/r2_l1_bench.txt (119.2 against 108.8 Gb/s, outputs identical).
 // Decodes L1_STREAMS random streams of L1_BITS message bits (s8 input, int16x2 core, 32-bit packs: the shape of BASELINE.json
 // configs[4]) in ONE launch with the product's 8-lane kernel (TBL=32 build, as the library picks for such launches) and with
 // the l1 kernel, compares the two outputs word for word and prints both times.  Random bytes are valid s8 symbols; both
