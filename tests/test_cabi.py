@@ -109,3 +109,13 @@ def test_one_lane_per_segment_geometry_cross_compiles(tmp_path):
             assert "0 bytes spill stores" in b, name
     sass = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
     assert "SHFL" not in sass and "LDGSTS" in sass and "VIMNMX" in sass
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md maps every C entry point to the reference interface it replaces (families by prefix)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    families = ("vit_comm_", "vit_job_", "vit_dev_", "vit_host_", "vit_stream_")
+    missing = [s for s in declared_symbols() if s not in doc and not s.startswith(families)]
+    assert not missing, missing
+    for fam in families:
+        assert fam in doc, fam
