@@ -250,25 +250,20 @@ def cpu_baseline(options, n_bits, snr, budget_s=12.0):
             "sample": "%d x full decode of a %d-bit stream (same options), OpenMP over the 6400 segments" % (reps, n_cpu)}
 
 
-def reference_cuda_baseline(options, n_bits, snr, reps=10):
+def reference_cuda_baseline(workload, reps=10):
     """The reference's own CUDA decoder (oracle/_ref/libvitref.so, the unmodified sources built for sm_100) timed in THIS run
-    on the same GPU, beside the CPU baseline: its own cudaEvent kernel time (viterbi.cu:224-232) on a stream of the same
-    options.  A reported baseline for the line (BASELINE.json: "three baselines timed on the same box in the same run");
-    the driver's ratio comes from the separate `--impl reference` arm.  Never raises: a failure is reported in the dict."""
+    on the same GPU, beside the CPU baseline (BASELINE.json: "three baselines timed on the same box in the same run"): the
+    reference arm of this script in a child process -- its run() answers a CUDA error with exit(), which must not be able to
+    cost this line.  A reported baseline; the driver's ratio comes from its own `--impl reference` run.  Never raises."""
     try:
-        from oracle import oracle as O
-        if O.ref_lib() is None or O.ref_lib().ref_device_count() <= 0:
-            return {"unavailable": "oracle/_ref/libvitref.so not built or no device"}
-        if not O.lib().vo_options_valid_ref(options):
-            return {"unavailable": "the reference rejects this option combination (viterbi.h:22-36)"}
-        n_ref = min(n_bits, 32_000_000)
-        bits, packed, N = O.make_channel(n_ref, options & 0xF, snr_db=snr, seed=5, prbs=True)
-        M = O.message_len(options, N)
-        for _ in range(3):
-            O.ref_decode(options, packed, N)
-        kms = [O.ref_decode(options, packed, N)[1] for _ in range(reps)]
-        return {"value": M / (statistics.mean(kms) * 1e6), "unit": "Gb/s", "kernel_ms": statistics.mean(kms), "kind": "reference CUDA decoder, -arch=sm_100",
-                "sample": "%d x ViterbiCUDA::run on a %d-bit stream (same options), its own cudaEvent kernel time" % (reps, n_ref)}
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                            "--steps", str(reps), "--warmup", "3"], capture_output=True, text=True, timeout=300,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        if line.get("cpu_baseline", {}).get("kind") != "reference":
+            return {"unavailable": line.get("note", "the reference's CUDA decoder did not run")}
+        return {"value": line["value"], "unit": "Gb/s", "kernel_ms": line["ms_per_step"], "e2e": line["e2e"]["value"],
+                "kind": "reference CUDA decoder, -arch=sm_100", "sample": line["cpu_baseline"]["sample"]}
     except Exception as e:          # a baseline must never cost the line
         return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
@@ -708,7 +703,7 @@ def main():
                               "value_by_wall_clock": M * S * world * args.steps / (ms_wall_max * 1e6)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(options, n_bits, snr)
-            line["reference_cuda"] = reference_cuda_baseline(options, n_bits, snr)
+            line["reference_cuda"] = reference_cuda_baseline(args.workload)
         print(json.dumps(line))
     dec.close()
     if comm is not None:

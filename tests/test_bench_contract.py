@@ -74,16 +74,17 @@ def test_clock_summary_flags_throttle_reasons():
 
 
 def test_same_run_reference_baseline_never_raises():
-    """bench.py's `reference_cuda` entry (the reference's CUDA decoder timed in the same run): without a device it reports
-    why it is unavailable instead of costing the line"""
+    """bench.py's `reference_cuda` entry (the reference's CUDA decoder timed in the same run, in a child process): without
+    a device it reports why it is unavailable instead of costing the line"""
     B = _bench()
     old = os.environ.get("CUDA_VISIBLE_DEVICES")
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     try:
-        r = B.reference_cuda_baseline(0x011, 32_000_000, 15.0)
+        r = B.reference_cuda_baseline("hard_b32_o32_1M", reps=3)
     finally:
         if old is None:
             del os.environ["CUDA_VISIBLE_DEVICES"]
         else:
             os.environ["CUDA_VISIBLE_DEVICES"] = old
-    assert "unavailable" in r or r["value"] > 0
+    assert "unavailable" in r and "golden model" in r["unavailable"]
+    assert "unavailable" in B.reference_cuda_baseline("no_such_workload")
