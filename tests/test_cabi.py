@@ -119,3 +119,28 @@ def test_integration_doc_lists_every_entry_point():
     assert not missing, missing
     for fam in families:
         assert fam in doc, fam
+
+
+def test_shipped_kernels_have_no_spills_and_the_expected_instructions():
+    """static facts of the built library (csrc/build/*.ptxas.log from the build, cuobjdump of the objects): all 76 decode
+    kernels without local memory, sm_100a SASS with the instructions the design rests on and none it must not have."""
+    build = os.path.join(PKG_DIR, "csrc", "build")
+    if not os.path.isdir(build):
+        pytest.skip("library not built here")
+    kernels = 0
+    for unit in ("b16", "b32", "b32d", "f16"):
+        log = open(os.path.join(build, "vit_inst_%s.ptxas.log" % unit)).read()
+        for block in re.split(r"Compiling entry function '", log)[1:]:
+            if "vit_decode_kernel" not in block.split("'")[0]:
+                continue
+            kernels += 1
+            assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in block, block[:200]
+            assert int(re.search(r"Used (\d+) registers", block).group(1)) <= 104        # >= 19 resident warps/SM by registers
+    assert kernels == 76                                                   # (28 + 10 option combinations) x 2 table builds
+    sass = subprocess.run(["cuobjdump", "-sass", os.path.join(build, "vit_inst_b16.o")], capture_output=True, text=True).stdout
+    for needle in ("VIMNMX.S16x2", "LDGSTS.E.BYPASS.128", "SHFL.BFLY", "STS.128", "LDS.64"):
+        assert needle in sass, needle
+    for absent in ("HMMA", "IMMA", "UTCHMMA", "UTMALDG", "LDL", "STL"):   # no tensor-core / TMA path by design, no local memory
+        assert absent not in sass, absent
+    sass32 = subprocess.run(["cuobjdump", "-sass", os.path.join(build, "vit_inst_b32.o")], capture_output=True, text=True).stdout
+    assert "VIADDMNMX" in sass32
