@@ -153,9 +153,11 @@ void emu_syncwarp();
 inline uint32_t shfl_xor(uint32_t v, int m) { return emu_shfl_xor(v, m); }
 inline uint32_t shfl_idx(uint32_t v, int src) { return emu_shfl_idx(v, src); }
 inline void syncwarp() { emu_syncwarp(); }
+void emu_note_global_read(const void* src, unsigned n);       // the emulator records which input bytes a lane requests
 inline void cp_async16(void* dst, const void* src, unsigned n) {
     uint8_t* d = (uint8_t*)dst;
     const uint8_t* s = (const uint8_t*)src;
+    if (n) emu_note_global_read(src, n);
     for (unsigned i = 0; i < 16; i++) d[i] = i < n ? s[i] : 0;
 }
 inline void cp_async_commit() {}

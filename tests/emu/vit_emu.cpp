@@ -48,6 +48,47 @@ uint32_t emu_shfl_idx(uint32_t v, int src) {
 void emu_syncwarp() { yield_next(); }
 }  // namespace vitk
 
+// ---- upload gates and the record of requested input bytes (tests/test_emu_kernel.py: the kernel side of vit_run's time-sliced
+// upload: a warp must not request channel words of a super-step whose gate is still closed) ----------------------------------
+namespace {
+unsigned g_gate_flags[8] = {};
+unsigned g_gate_err = 0;
+unsigned g_gate_n = 0, g_gate_super[8] = {};
+const uint8_t* g_in_base = nullptr;
+unsigned g_cur_warp = 0, g_cur_lanes = 8;
+struct ReadRec { unsigned seg; unsigned long long off; unsigned n; };
+ReadRec* g_reads = nullptr;
+size_t g_nreads = 0, g_reads_cap = 0;
+}  // namespace
+namespace vitk {
+void emu_note_global_read(const void* src, unsigned n) {
+    if (!g_reads || g_nreads >= g_reads_cap) return;
+    const unsigned seg = g_cur_warp * (32 / g_cur_lanes) + (unsigned)g_cur / g_cur_lanes;
+    g_reads[g_nreads++] = ReadRec{seg, (unsigned long long)((const uint8_t*)src - g_in_base), n};
+}
+}  // namespace vitk
+extern "C" void vit_emu_set_gates(unsigned n, const unsigned* super, unsigned open_count) {
+    g_gate_n = n > 8 ? 8 : n;
+    for (unsigned i = 0; i < 8; i++) { g_gate_super[i] = i < g_gate_n ? super[i] : 0; g_gate_flags[i] = i < open_count ? 1u : 0u; }
+    g_gate_err = 0;
+}
+extern "C" unsigned vit_emu_gate_error() { return g_gate_err; }
+// start (cap_records > 0) or stop (0) recording the input reads of the following decodes; fetch returns them as
+// (segment, byte offset in the stream, bytes) triples of uint64
+extern "C" void vit_emu_record_reads(size_t cap_records) {
+    static ReadRec* store = nullptr;
+    static size_t store_cap = 0;
+    g_reads = nullptr; g_nreads = 0; g_reads_cap = 0;
+    if (!cap_records) return;
+    if (store_cap < cap_records) { free(store); store = (ReadRec*)malloc(sizeof(ReadRec) * cap_records); store_cap = cap_records; }
+    g_reads = store; g_reads_cap = cap_records;
+}
+extern "C" size_t vit_emu_fetch_reads(unsigned long long* buf, size_t cap_records) {
+    const size_t n = g_nreads < cap_records ? g_nreads : cap_records;
+    for (size_t i = 0; i < n; i++) { buf[3 * i] = g_reads[i].seg; buf[3 * i + 1] = g_reads[i].off; buf[3 * i + 2] = g_reads[i].n; }
+    return g_nreads;
+}
+
 namespace {
 struct Job {
     vitk::KParams kp;
@@ -140,6 +181,9 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     g_job.kp.in = (const uint8_t*)in; g_job.kp.out = (uint8_t*)out;
     g_job.kp.in_stride = in_stride; g_job.kp.out_stride = out_stride;
     g_job.kp.in_bytes = in_bytes; g_job.kp.packs = M / bpp;
+    g_job.kp.gate = g_gate_flags; g_job.kp.gate_err = &g_gate_err; g_job.kp.gate_epoch = 1u; g_job.kp.gate_n = g_gate_n; g_job.kp.gate_timeout_ns = 0;
+    for (int i = 0; i < 8; i++) g_job.kp.gate_super[i] = g_gate_super[i];
+    g_in_base = (const uint8_t*)in; g_cur_lanes = (unsigned)g_job.lanes;
     g_job.kp.segments = segments; g_job.kp.seg_first = 0; g_job.kp.seg_limit = segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u; g_job.kp.stage_out = g_stage_out;
     g_job.met = mt == 0 ? (((options >> 12) & 0xf) == 2 ? vitk::MET_B32D : vitk::MET_B32) : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
     g_job.in = it; g_job.bpp = bpp;
@@ -148,7 +192,7 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     unsigned nwarps = (segments + spw - 1) / spw;
     for (unsigned s = 0; s < nstreams; s++)
         for (unsigned w = 0; w < nwarps; w++) {
-            g_job.warp = w; g_job.stream = s;
+            g_job.warp = w; g_job.stream = s; g_cur_warp = w;
             memset(g_job.smem, 0xA5, 64 * 1024);   // catch reads of unwritten shared memory
             run_warp();
         }

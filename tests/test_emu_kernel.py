@@ -196,3 +196,68 @@ def test_kernel_source_one_lane_per_segment_geometry(emu, O, opt):
         run_case(emu, O, opt, 40 * 32 * 70 + 64 + 5, 70, seed=3, sigma=0.8)
     finally:
         emu.vit_emu_set_lanes(8)
+
+
+def _gate_case(emu, O, opt, n, W, sup, open_count):
+    """decode with upload gates `sup` of which the first open_count are open; returns (out, reference, reads, gate error)"""
+    import ctypes as C
+    bits, packed, N = O.make_channel_det(n, opt & 0xF, seed=17, sigma=0.8)
+    O.set_segments(W)
+    try:
+        ref = O.decode(opt, packed, N)
+    finally:
+        O.set_segments(0)
+    arr = (C.c_uint * len(sup))(*sup)
+    emu.vit_emu_set_gates(len(sup), arr, open_count)
+    emu.vit_emu_record_reads(1 << 20)
+    try:
+        packed = np.ascontiguousarray(packed)
+        buf = np.zeros((packed.nbytes + 31) // 16 * 16 + 16, np.uint8)
+        off = (-buf.ctypes.data) % 16
+        buf[off:off + packed.nbytes] = packed.view(np.uint8)
+        nw = O.output_size(opt, N) // np.dtype(O.out_dtype(opt)).itemsize
+        out = np.full(nw + 4, 0xDEAD, O.out_dtype(opt))
+        assert emu.vit_emu_decode(opt, buf[off:].ctypes.data, out.ctypes.data, N, W, 1, 0, 0) == 0
+        rec = np.zeros(3 << 20, np.uint64)
+        cnt = emu.vit_emu_fetch_reads(rec.ctypes.data, 1 << 20)
+        assert cnt <= 1 << 20
+        return out[:nw], ref, rec[:3 * cnt].reshape(-1, 3).astype(np.int64), emu.vit_emu_gate_error(), N
+    finally:
+        emu.vit_emu_set_gates(0, (C.c_uint * 1)(0), 0)
+        emu.vit_emu_record_reads(0)
+
+
+@pytest.mark.parametrize("opt", [0x011, 0x000, 0x112, 0x004])
+def test_kernel_source_respects_upload_gates(emu, O, opt):
+    """The kernel side of vit_run's time-sliced upload (the host side: tests/test_upload_plan_model.py).  A warp passes gate g
+    before it requests the channel words of any super-step x >= gate_super[g].  With every gate open the output is the
+    golden model's; with gates 1.. closed the warps stop (and report it), and NO input byte at or beyond the column the
+    host uploads with the closed gate's block has been requested: per segment, every requested byte lies in columns
+    [-15, gate_super[k] * b96 + 48) of its row -- exactly what blocks 0..k-1 of run_gated have delivered."""
+    import ctypes as C
+    emu.vit_emu_record_reads.argtypes = [C.c_size_t]
+    emu.vit_emu_fetch_reads.restype, emu.vit_emu_fetch_reads.argtypes = C.c_size_t, [C.c_void_p, C.c_size_t]
+    emu.vit_emu_set_gates.argtypes = [C.c_uint, C.c_void_p, C.c_uint]
+    emu.vit_emu_gate_error.restype = C.c_uint
+    it, bpp = opt & 0xF, (16 if opt & 0x100 else 32)
+    b96 = {0: 24, 1: 96, 2: 192, 3: 384, 4: 768}[it]
+    W, packs = 12, 12 * 40 + 5                                    # 40-41 packs per segment: 14-15 super-steps
+    n = packs * bpp + 64 + 3
+    nsuper = (64 + 32 * ((41 * bpp + 31) // 32) + 95) // 96
+    sup = [0, nsuper // 2, nsuper * 7 // 8]
+    out, ref, reads, err, N = _gate_case(emu, O, opt, n, W, sup, 3)
+    assert err == 0 and np.array_equal(out, ref)                  # all gates open: nothing changes
+    P = O.message_len(opt, N) // bpp
+    q, r = divmod(P, W)
+    pack_bytes = bpp * b96 // 96
+    rows = np.array([(q * w + min(w, r)) * pack_bytes for w in range(W)], np.int64)
+    for open_count in (1, 2):
+        out, ref, reads, err, N = _gate_case(emu, O, opt, n, W, sup, open_count)
+        assert err == 1                                           # the warps gave up at the closed gate and said so
+        limit = sup[open_count] * b96 + 48
+        col = reads[:, 1] - rows[reads[:, 0]]
+        assert len(reads) > 0 and col.min() >= -15
+        assert (col + reads[:, 2]).max() <= limit, (open_count, int((col + reads[:, 2]).max()), limit)
+        assert (col + reads[:, 2]).max() > (sup[open_count] - 1) * b96     # ... and they did get as far as the gate allows
+        written = out != 0xDEAD
+        assert np.array_equal(out[written], ref[written])        # whatever was emitted before the stop is correct
