@@ -162,6 +162,9 @@ void run_warp() {
 extern "C" void vit_emu_polynomials(int* p1, int* p2) { *p1 = vitk::POLY1; *p2 = vitk::POLY2; }
 
 static unsigned g_stage_out = 0;
+static unsigned g_seg_first = 0, g_seg_limit = 0;   // 0, 0: the whole stream
+// decode only segments [first, limit) in the following calls (the segment-range launches of vit_run's chunk pipeline)
+extern "C" void vit_emu_set_segment_range(unsigned first, unsigned limit) { g_seg_first = first; g_seg_limit = limit; }
 extern "C" void vit_emu_set_stage_out(int on) { g_stage_out = on ? 1u : 0u; }
 extern "C" void vit_emu_set_table(int tbl) { g_job.tbl = tbl == 32 ? 32 : 96; }
 #if defined(VIT_EMU_L8_ONLY)
@@ -184,12 +187,12 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     g_job.kp.gate = g_gate_flags; g_job.kp.gate_err = &g_gate_err; g_job.kp.gate_epoch = 1u; g_job.kp.gate_n = g_gate_n; g_job.kp.gate_timeout_ns = 0;
     for (int i = 0; i < 8; i++) g_job.kp.gate_super[i] = g_gate_super[i];
     g_in_base = (const uint8_t*)in; g_cur_lanes = (unsigned)g_job.lanes;
-    g_job.kp.segments = segments; g_job.kp.seg_first = 0; g_job.kp.seg_limit = segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u; g_job.kp.stage_out = g_stage_out;
+    g_job.kp.segments = segments; g_job.kp.seg_first = g_seg_limit ? g_seg_first : 0; g_job.kp.seg_limit = g_seg_limit ? g_seg_limit : segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u; g_job.kp.stage_out = g_stage_out;
     g_job.met = mt == 0 ? (((options >> 12) & 0xf) == 2 ? vitk::MET_B32D : vitk::MET_B32) : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
     g_job.in = it; g_job.bpp = bpp;
     g_job.smem = (uint8_t*)aligned_alloc(128, 64 * 1024);
     const unsigned spw = 32 / g_job.lanes;
-    unsigned nwarps = (segments + spw - 1) / spw;
+    unsigned nwarps = (g_job.kp.seg_limit - g_job.kp.seg_first + spw - 1) / spw;
     for (unsigned s = 0; s < nstreams; s++)
         for (unsigned w = 0; w < nwarps; w++) {
             g_job.warp = w; g_job.stream = s; g_cur_warp = w;

@@ -261,3 +261,40 @@ def test_kernel_source_respects_upload_gates(emu, O, opt):
         assert (col + reads[:, 2]).max() > (sup[open_count] - 1) * b96     # ... and they did get as far as the gate allows
         written = out != 0xDEAD
         assert np.array_equal(out[written], ref[written])        # whatever was emitted before the stop is correct
+
+
+@pytest.mark.parametrize("opt", [0x011, 0x112, 0x000])
+def test_kernel_source_segment_range_launches(emu, O, opt):
+    """vit_run's chunk pipeline decodes a stream with several launches over segment ranges [seg_first, seg_limit) (cut at
+    multiples of 8 segments).  Each launch must write exactly the packs its segments own, and together they must give the
+    one-launch output."""
+    import ctypes as C
+    emu.vit_emu_set_segment_range.argtypes = [C.c_uint, C.c_uint]
+    bpp = 16 if opt & 0x100 else 32
+    W, n = 40, (40 * 9 + 13) * bpp + 64 + 5              # the first 13 segments are one pack longer
+    bits, packed, N = O.make_channel_det(n, opt & 0xF, seed=23, sigma=0.8)
+    O.set_segments(W)
+    try:
+        ref = O.decode(opt, packed, N)
+    finally:
+        O.set_segments(0)
+    P = O.message_len(opt, N) // bpp
+    q, r = divmod(P, W)
+    start = lambda w: q * w + min(w, r)
+    packed = np.ascontiguousarray(packed)
+    buf = np.zeros((packed.nbytes + 31) // 16 * 16 + 16, np.uint8)
+    off = (-buf.ctypes.data) % 16
+    buf[off:off + packed.nbytes] = packed.view(np.uint8)
+    total = np.full(ref.size, 0xDEAD, ref.dtype)
+    try:
+        for a, b in ((0, 8), (8, 24), (24, 40)):
+            out = np.full(ref.size + 4, 0xDEAD, ref.dtype)
+            emu.vit_emu_set_segment_range(a, b)
+            assert emu.vit_emu_decode(opt, buf[off:].ctypes.data, out.ctypes.data, N, W, 1, 0, 0) == 0
+            lo, hi = start(a), (start(b) if b < W else P)
+            assert np.array_equal(out[lo:hi], ref[lo:hi]), (a, b)
+            assert np.all(out[:lo] == 0xDEAD) and np.all(out[hi:] == 0xDEAD), (a, b)     # nothing outside its own range
+            total[lo:hi] = out[lo:hi]
+    finally:
+        emu.vit_emu_set_segment_range(0, 0)
+    assert np.array_equal(total, ref)
