@@ -161,6 +161,7 @@ void run_warp() {
 // the generator polynomials this emulator build was compiled for (-DVIT_POLY1= / -DVIT_POLY2=, csrc/vit_code.h)
 extern "C" void vit_emu_polynomials(int* p1, int* p2) { *p1 = vitk::POLY1; *p2 = vitk::POLY2; }
 
+static void run_grid();
 static unsigned g_stage_out = 0;
 static unsigned g_seg_first = 0, g_seg_limit = 0;   // 0, 0: the whole stream
 // decode only segments [first, limit) in the following calls (the segment-range launches of vit_run's chunk pipeline)
@@ -190,15 +191,30 @@ extern "C" int vit_emu_decode(int options, const void* in, void* out, size_t inp
     g_job.kp.segments = segments; g_job.kp.seg_first = g_seg_limit ? g_seg_first : 0; g_job.kp.seg_limit = g_seg_limit ? g_seg_limit : segments; g_job.kp.nstreams = nstreams; g_job.kp.one = 1u; g_job.kp.stage_out = g_stage_out;
     g_job.met = mt == 0 ? (((options >> 12) & 0xf) == 2 ? vitk::MET_B32D : vitk::MET_B32) : mt == 1 ? vitk::MET_B16 : vitk::MET_F16;
     g_job.in = it; g_job.bpp = bpp;
+    run_grid();
+    return 0;
+}
+
+// every warp of the launch g_job describes (grid = segment groups x streams), one after the other
+static void run_grid() {
     g_job.smem = (uint8_t*)aligned_alloc(128, 64 * 1024);
     const unsigned spw = 32 / g_job.lanes;
-    unsigned nwarps = (g_job.kp.seg_limit - g_job.kp.seg_first + spw - 1) / spw;
-    for (unsigned s = 0; s < nstreams; s++)
+    const unsigned nwarps = (g_job.kp.seg_limit - g_job.kp.seg_first + spw - 1) / spw;
+    for (unsigned s = 0; s < g_job.kp.nstreams; s++)
         for (unsigned w = 0; w < nwarps; w++) {
             g_job.warp = w; g_job.stream = s; g_cur_warp = w;
             memset(g_job.smem, 0xA5, 64 * 1024);   // catch reads of unwritten shared memory
             run_warp();
         }
     free(g_job.smem);
-    return 0;
+}
+
+// a launch exactly as the library's host code describes it (tests/sim: csrc/vit_api.cu compiled for the host hands its
+// KParams to the emulator instead of a GPU); product lane geometry, operand-table build `tbl`
+void vit_emu_run_kparams(const vitk::KParams& kp, int met, int in, int bpp, int tbl) {
+    g_job.kp = kp;
+    g_job.met = met; g_job.in = in; g_job.bpp = bpp;
+    g_job.lanes = 8; g_job.tbl = tbl == 32 ? 32 : 96;
+    g_in_base = kp.in; g_cur_lanes = 8;
+    run_grid();
 }

@@ -1,0 +1,179 @@
+"""CPU run of the library's HOST code (csrc/vit_api.cu itself, compiled with a plain C++ compiler) against the kernel
+SOURCE in the host emulator, through a stand-in CUDA runtime (tests/sim: test scaffolding, see sim_runtime.cpp).
+
+The stand-in runtime schedules adversarially: "device" memory starts as garbage, a chunk-pipeline kernel runs the moment
+its own chunk's bytes have been copied (later uploads are not even enqueued yet), and the gate-waiting kernel of the
+time-sliced upload is re-run from scratch at EVERY gate opening with the memory as it is then -- whatever such a partial run
+emits must already be final (sim_violations).  So vit_run's paths (sequential, time-sliced with pinned / pageable / mixed
+buffers incl. the worker-pool staging, the segment-range chunk pipeline) and vit_stream_push are executed for real --
+geometry, strided copies, gates, staging, downloads, carry arithmetic -- and compared with the golden model, over more
+stream shapes than the GPU suite samples.  The product has no CPU path: this library exists only in the tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from vit_testlib import PKG_DIR, ROOT
+
+SIM = os.path.join(ROOT, "tests", "sim")
+SEQUENTIAL, CHUNKED, GATED = 1, 2, 3
+W = 64                       # segments (vit_set_segments): the smallest count the overlapped paths accept
+
+
+@pytest.fixture(scope="module")
+def sim():
+    so = os.path.join(SIM, "libvitsim.so")
+    srcs = [os.path.join(PKG_DIR, "csrc", f) for f in ("vit_api.cu", "vit_kernel.cuh", "vit_kernel_map.inc", "vit_stage_pool.h", "vit_launch.h", "vit_code.h")]
+    srcs += [os.path.join(SIM, "sim_runtime.cpp"), os.path.join(SIM, "cuda_runtime.h"), os.path.join(ROOT, "tests", "emu", "vit_emu.cpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIT_EMU_L8_ONLY", "-I", SIM, "-x", "c++",
+                               srcs[0], os.path.join(SIM, "sim_runtime.cpp"), os.path.join(ROOT, "tests", "emu", "vit_emu.cpp"), "-o", so])
+    L = C.CDLL(so)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.vit_create.restype, L.vit_create.argtypes = C.c_int, [C.POINTER(vp), C.c_int, C.c_int, sz]
+    L.vit_destroy.restype, L.vit_destroy.argtypes = None, [vp]
+    L.vit_run.restype, L.vit_run.argtypes = C.c_int, [vp, vp, vp, sz, C.POINTER(C.c_float)]
+    L.vit_set_segments.restype, L.vit_set_segments.argtypes = C.c_int, [vp, C.c_uint]
+    L.vit_set_upload_mode.restype, L.vit_set_upload_mode.argtypes = C.c_int, [vp, C.c_int]
+    L.vit_upload_mode_in_effect.restype, L.vit_upload_mode_in_effect.argtypes = C.c_int, [vp]
+    L.vit_launch_count.restype, L.vit_launch_count.argtypes = C.c_ulonglong, [vp]
+    L.vit_last_error.restype = C.c_char_p
+    L.vit_stream_reset.restype, L.vit_stream_reset.argtypes = C.c_int, [vp]
+    L.vit_stream_push.restype, L.vit_stream_push.argtypes = C.c_int, [vp, vp, sz, vp, sz, C.POINTER(sz)]
+    L.vit_stream_pending.restype, L.vit_stream_pending.argtypes = sz, [vp]
+    L.sim_pinned_alloc.restype, L.sim_pinned_alloc.argtypes = vp, [sz]
+    L.sim_pinned_free.restype, L.sim_pinned_free.argtypes = None, [vp]
+    for f in ("sim_violations", "sim_kernel_runs", "sim_gated_attempts"):
+        getattr(L, f).restype = C.c_ulonglong
+    L.sim_set_table.argtypes = [C.c_int]
+    return L
+
+
+class Pinned:
+    """a numpy view of page-locked memory as the stand-in runtime knows it (is_pinned() -> true)"""
+    def __init__(self, L, nbytes):
+        self.L, self.p = L, L.sim_pinned_alloc(nbytes)
+        self.a = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.p))
+
+    def free(self):
+        self.L.sim_pinned_free(self.p)
+
+
+def _make(L, opt):
+    h = C.c_void_p()
+    assert L.vit_create(C.byref(h), opt, 0, 0) == 0, L.vit_last_error()
+    assert L.vit_set_segments(h, W) == 0
+    return h
+
+
+def _run(L, O, h, opt, n_bits, seed, mode, pin_in, pin_out, sigma=0.8):
+    bits, packed, N = O.make_channel_det(n_bits, opt & 0xF, seed=seed, sigma=sigma)
+    O.set_segments(W)
+    try:
+        exp = O.decode(opt, packed, N)
+    finally:
+        O.set_segments(0)
+    in_bytes, out_bytes = O.input_size(opt, N), O.output_size(opt, N)
+    raw = np.ascontiguousarray(packed).view(np.uint8)[:in_bytes]
+    bi = Pinned(L, in_bytes) if pin_in else None
+    bo = Pinned(L, out_bytes) if pin_out else None
+    src = bi.a if pin_in else raw.copy()
+    if pin_in:
+        src[:] = raw
+    dst = bo.a if pin_out else np.zeros(out_bytes, np.uint8)
+    dst[:] = 0x5A
+    assert L.vit_set_upload_mode(h, mode) == 0
+    rc = L.vit_run(h, src.ctypes.data, dst.ctypes.data, N, None)
+    assert rc == 0, L.vit_last_error()
+    got = dst.view(exp.dtype).copy()
+    for b in (bi, bo):
+        if b:
+            b.free()
+    return got, exp
+
+
+# (options, message bits): 20+ packs per segment -> >= 8 super-steps (the forced time-sliced mode needs them); ragged
+# counts, 16-bit packs with odd tails, hard input (24 channel bytes per super-step), fp32
+SHAPES = [
+    (0x011, (W * 22 + 7) * 32 + 64 + 5),
+    (0x011, (W * 31) * 32 + 64),
+    (0x000, (W * 26 + 63) * 32 + 64 + 31),
+    (0x112, (W * 45 + 3) * 16 + 64 + 9),
+    (0x100, (W * 47 + 33) * 16 + 64),
+    (0x004, (W * 21 + 1) * 32 + 64 + 2),
+    (0x022, (W * 24 + 40) * 32 + 64),
+    (0x2003, (W * 23 + 11) * 32 + 64),
+]
+
+
+@pytest.mark.parametrize("opt,n_bits", SHAPES)
+def test_time_sliced_upload_host_code_on_the_cpu(sim, O, opt, n_bits):
+    """vit_run in the forced time-sliced mode: one launch per call, every pinned / pageable mix (the pageable sides go
+    through the worker pool and the pinned staging buffers), output equal to the golden model, and no partial run of the
+    gate-waiting kernel ever emitted a word that differed from the final one."""
+    L = sim
+    h = _make(L, opt)
+    L.sim_reset_counters()
+    launches = L.vit_launch_count(h)
+    for k, (pi, po) in enumerate(((True, True), (False, False), (True, False), (False, True))):
+        got, exp = _run(L, O, h, opt, n_bits, 100 + k, GATED, pi, po)
+        assert np.array_equal(got, exp), (hex(opt), pi, po)
+    assert L.vit_launch_count(h) - launches == 4                  # ONE launch per call: no fallback happened
+    assert L.vit_upload_mode_in_effect(h) == GATED
+    assert L.sim_violations() == 0
+    assert L.sim_gated_attempts() >= 4 * 2                        # the kernel was re-run at the gate openings (2-4 gates per call)
+    L.vit_destroy(h)
+
+
+@pytest.mark.parametrize("opt,n_bits", SHAPES[:4])
+def test_sequential_path_and_small_table_build(sim, O, opt, n_bits):
+    L = sim
+    h = _make(L, opt)
+    for tbl in (96, 32):
+        L.sim_set_table(tbl)
+        try:
+            got, exp = _run(L, O, h, opt, n_bits, 7 + tbl, SEQUENTIAL, False, False)
+            assert np.array_equal(got, exp), (hex(opt), tbl)
+            got, exp = _run(L, O, h, opt, n_bits // 3, 9 + tbl, GATED, True, True)     # growing then shrinking inputs on one handle
+            assert np.array_equal(got, exp), (hex(opt), tbl)
+        finally:
+            L.sim_set_table(96)
+    L.vit_destroy(h)
+
+
+@pytest.mark.parametrize("opt", [0x011, 0x100, 0x004])
+def test_stream_push_host_code_on_the_cpu(sim, O, opt):
+    """vit_stream_push: windows = carried symbols ++ chunk, decoded like a run() of the window; the carry arithmetic and the
+    device-side tail copies are the library's own code here.  Compared push by push with the oracle's restatement."""
+    L = sim
+    it = opt & 0xF
+    spw = {0: 32, 1: 8, 2: 4, 3: 2, 4: 1}[it]
+    h = _make(L, opt)
+    n_bits = 40_000
+    bits, packed, N = O.make_channel_det(n_bits, it, seed=5, sigma=0.7)
+    words = np.ascontiguousarray(packed).view(np.uint32)
+    rng = np.random.default_rng(opt)
+    cuts = sorted(set(int(x) for x in rng.integers(1, words.size, 9)) | {3, words.size})
+    chunks, prev = [], 0
+    for c in cuts:
+        chunks.append((prev, c))
+        prev = c
+    O.set_segments(W)
+    try:
+        exp, pending = O.decode_chunked(opt, packed, [(b - a) * spw for a, b in chunks])
+    finally:
+        O.set_segments(0)
+    assert L.vit_stream_reset(h) == 0
+    itemsize = 2 if opt & 0x100 else 4
+    for (a, b), e in zip(chunks, exp):
+        buf = np.zeros(e.size * itemsize + 64, np.uint8)
+        nout = C.c_size_t(0)
+        chunk = words[a:b].copy()
+        assert L.vit_stream_push(h, chunk.ctypes.data, (b - a) * spw, buf.ctypes.data, buf.size, C.byref(nout)) == 0, L.vit_last_error()
+        assert nout.value == e.size * itemsize
+        assert np.array_equal(buf[:nout.value].view(e.dtype), e), (a, b)
+    assert L.vit_stream_pending(h) == pending
+    L.vit_destroy(h)
