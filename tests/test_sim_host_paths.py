@@ -177,3 +177,18 @@ def test_stream_push_host_code_on_the_cpu(sim, O, opt):
         assert np.array_equal(buf[:nout.value].view(e.dtype), e), (a, b)
     assert L.vit_stream_pending(h) == pending
     L.vit_destroy(h)
+
+
+def test_chunk_pipeline_host_code_on_the_cpu(sim, O):
+    """vit_run's segment-range chunk pipeline (pinned buffers where gates cannot be used): 8.4 MB of fp32 input = two
+    chunks.  The stand-in runtime runs chunk 0's kernel the moment chunk 0's bytes are copied -- chunk 1's upload has not
+    even been enqueued and its part of the device buffer is still garbage -- so the byte range vit_run uploads per chunk
+    must cover everything that chunk's segments read."""
+    L = sim
+    opt, n_bits = 0x004, (W * 512 + 17) * 32 + 64 + 3
+    h = _make(L, opt)
+    launches = L.vit_launch_count(h)
+    got, exp = _run(L, O, h, opt, n_bits, 41, CHUNKED, True, True)
+    assert np.array_equal(got, exp)
+    assert L.vit_launch_count(h) - launches == 2
+    L.vit_destroy(h)
