@@ -12,7 +12,7 @@ import pytest
 from test_emu_kernel import emu_decode
 
 # (polyn1, polyn2): the bit-reversed standard code; the standard pair in the other order; another pair tapping both ends
-PAIRS = [(0o117, 0o155), (0o133, 0o171)]
+from vit_testlib import ALT_EMU_PAIRS as PAIRS  # noqa: E402
 OPTS = [0x011, 0x000, 0x121, 0x112, 0x004, 0x022, 0x2001]
 
 

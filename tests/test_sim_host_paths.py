@@ -10,7 +10,6 @@ geometry, strided copies, gates, staging, downloads, carry arithmetic -- and com
 stream shapes than the GPU suite samples.  The product has no CPU path: this library exists only in the tests."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -23,14 +22,8 @@ W = 64                       # segments (vit_set_segments): the smallest count t
 
 
 @pytest.fixture(scope="module")
-def sim():
-    so = os.path.join(SIM, "libvitsim.so")
-    srcs = [os.path.join(PKG_DIR, "csrc", f) for f in ("vit_api.cu", "vit_kernel.cuh", "vit_kernel_map.inc", "vit_stage_pool.h", "vit_launch.h", "vit_code.h")]
-    srcs += [os.path.join(SIM, "sim_runtime.cpp"), os.path.join(SIM, "cuda_runtime.h"), os.path.join(ROOT, "tests", "emu", "vit_emu.cpp")]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.check_call([gxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIT_EMU_L8_ONLY", "-I", SIM, "-x", "c++",
-                               srcs[0], os.path.join(SIM, "sim_runtime.cpp"), os.path.join(ROOT, "tests", "emu", "vit_emu.cpp"), "-o", so])
+def sim(sim_lib_path):
+    so = sim_lib_path
     L = C.CDLL(so)
     vp, sz = C.c_void_p, C.c_size_t
     L.vit_create.restype, L.vit_create.argtypes = C.c_int, [C.POINTER(vp), C.c_int, C.c_int, sz]

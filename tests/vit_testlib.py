@@ -23,6 +23,8 @@ def load_pkg():
     return mod
 
 
+# generator-polynomial pairs the emulator is also built for (tests/test_code_parameters.py)
+ALT_EMU_PAIRS = [(0o117, 0o155), (0o133, 0o171)]
 ALT_POLYS = (0o117, 0o155)
 ALT_LIB = os.path.join(PKG_DIR, "libvitb200_p%o_%o.so" % ALT_POLYS)
 
