@@ -185,3 +185,29 @@ def test_chunk_pipeline_host_code_on_the_cpu(sim, O):
     assert np.array_equal(got, exp)
     assert L.vit_launch_count(h) - launches == 2
     L.vit_destroy(h)
+
+
+def test_host_paths_fuzz(sim, O):
+    """seeded fuzz of vit_run over stream shapes, option values, upload modes and buffer kinds, one handle per option value
+    kept across calls (device / staging buffers grow and are reused); 12 s"""
+    import time
+    L = sim
+    rng = np.random.default_rng(20261019)
+    opts = [0x011, 0x000, 0x112, 0x101, 0x002, 0x021, 0x2000]
+    handles = {o: _make(L, o) for o in opts}
+    L.sim_reset_counters()
+    t0, cases = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 12.0:
+        opt = opts[int(rng.integers(len(opts)))]
+        bpp = 16 if opt & 0x100 else 32
+        packs_per_seg = int(rng.integers(20, 34)) * (32 // bpp)
+        n_bits = (W * packs_per_seg + int(rng.integers(0, W))) * bpp + 64 + int(rng.integers(0, bpp))
+        mode = GATED if rng.random() < 0.8 else SEQUENTIAL
+        pi, po = bool(rng.integers(2)), bool(rng.integers(2))
+        got, exp = _run(L, O, handles[opt], opt, n_bits, int(rng.integers(1, 1 << 30)), mode, pi, po, sigma=float(rng.choice([0.3, 0.8, 1.5])))
+        assert np.array_equal(got, exp), (hex(opt), n_bits, mode, pi, po)
+        cases += 1
+    assert L.sim_violations() == 0 and cases >= 5, cases
+    for h in handles.values():
+        assert L.vit_upload_mode_in_effect(h) in (GATED, SEQUENTIAL)
+        L.vit_destroy(h)
