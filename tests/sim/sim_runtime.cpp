@@ -153,24 +153,47 @@ const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no er
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+// Every allocation sits between two 256-byte canaries (0xC5) that are checked when it is freed (and by sim_check_canaries):
+// a write outside a device or pinned buffer -- by the host code's copies or by an emulated kernel -- counts as a violation.
+static char* guarded_alloc(std::map<const char*, size_t>& reg, size_t n, int fill) {
+    char* raw = static_cast<char*>(aligned_alloc(256, (n + 768 + 255) / 256 * 256));
+    if (!raw) return nullptr;
+    memset(raw, 0xC5, 256);
+    memset(raw + 256, fill, n);
+    memset(raw + 256 + n, 0xC5, 512);                         // (n + 768 bytes in all)
+    reg[raw + 256] = n;
+    return raw + 256;
+}
+static void check_canaries(const char* user, size_t n) {
+    const unsigned char* lo = reinterpret_cast<const unsigned char*>(user) - 256;
+    const unsigned char* hi = reinterpret_cast<const unsigned char*>(user) + n;
+    for (int i = 0; i < 256; i++) if (lo[i] != 0xC5 || hi[i] != 0xC5) { g_violations++; return; }
+}
+static void guarded_free(std::map<const char*, size_t>& reg, void* p) {
+    auto it = reg.find(static_cast<const char*>(p));
+    if (it == reg.end()) { g_violations++; return; }          // not ours, or freed twice
+    check_canaries(it->first, it->second);
+    reg.erase(it);
+    free(static_cast<char*>(p) - 256);
+}
+extern "C" void sim_check_canaries(void) {
+    for (const auto& kv : g_device) check_canaries(kv.first, kv.second);
+    for (const auto& kv : g_pinned) check_canaries(kv.first, kv.second);
+}
 cudaError_t cudaMalloc(void** p, size_t n) {
-    char* m = static_cast<char*>(aligned_alloc(256, (n + 255) / 256 * 256 + 256));
+    char* m = guarded_alloc(g_device, n, 0xCD);              // not-yet-uploaded bytes are garbage
     if (!m) return cudaErrorMemoryAllocation;
-    memset(m, 0xCD, (n + 255) / 256 * 256 + 256);          // not-yet-uploaded bytes are garbage
-    g_device[m] = n;
     *p = m;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { if (p) { pump(true); g_device.erase(static_cast<const char*>(p)); free(p); } return cudaSuccess; }
+cudaError_t cudaFree(void* p) { if (p) { pump(true); guarded_free(g_device, p); } return cudaSuccess; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
-    char* m = static_cast<char*>(aligned_alloc(256, (n + 255) / 256 * 256 + 256));
+    char* m = guarded_alloc(g_pinned, n, 0xAB);
     if (!m) return cudaErrorMemoryAllocation;
-    memset(m, 0xAB, (n + 255) / 256 * 256 + 256);
-    g_pinned[m] = n;
     *p = m;
     return cudaSuccess;
 }
-cudaError_t cudaFreeHost(void* p) { if (p) { pump(true); g_pinned.erase(static_cast<const char*>(p)); free(p); } return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { if (p) { pump(true); guarded_free(g_pinned, p); } return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
 cudaError_t cudaMemset(void* p, int v, size_t n) { pump(true); memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {

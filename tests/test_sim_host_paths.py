@@ -42,7 +42,18 @@ def sim(sim_lib_path):
     for f in ("sim_violations", "sim_kernel_runs", "sim_gated_attempts"):
         getattr(L, f).restype = C.c_ulonglong
     L.sim_set_table.argtypes = [C.c_int]
+    L.sim_check_canaries.restype = None
     return L
+
+
+@pytest.fixture(autouse=True)
+def no_violations(sim):
+    """every test: no partial run emitted a non-final word, and nothing wrote outside a device or pinned buffer (the
+    stand-in runtime keeps canaries around every allocation and checks them when it is freed)"""
+    sim.sim_reset_counters()
+    yield
+    sim.sim_check_canaries()
+    assert sim.sim_violations() == 0
 
 
 class Pinned:
@@ -116,6 +127,7 @@ def test_time_sliced_upload_host_code_on_the_cpu(sim, O, opt, n_bits):
         assert np.array_equal(got, exp), (hex(opt), pi, po)
     assert L.vit_launch_count(h) - launches == 4                  # ONE launch per call: no fallback happened
     assert L.vit_upload_mode_in_effect(h) == GATED
+    L.sim_check_canaries()                                          # no write outside any device / pinned buffer
     assert L.sim_violations() == 0
     assert L.sim_gated_attempts() >= 4 * 2                        # the kernel was re-run at the gate openings (2-4 gates per call)
     L.vit_destroy(h)
@@ -207,6 +219,7 @@ def test_host_paths_fuzz(sim, O):
         got, exp = _run(L, O, handles[opt], opt, n_bits, int(rng.integers(1, 1 << 30)), mode, pi, po, sigma=float(rng.choice([0.3, 0.8, 1.5])))
         assert np.array_equal(got, exp), (hex(opt), n_bits, mode, pi, po)
         cases += 1
+    L.sim_check_canaries()
     assert L.sim_violations() == 0 and cases >= 5, cases
     for h in handles.values():
         assert L.vit_upload_mode_in_effect(h) in (GATED, SEQUENTIAL)
