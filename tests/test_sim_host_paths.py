@@ -224,3 +224,39 @@ def test_host_paths_fuzz(sim, O):
     for h in handles.values():
         assert L.vit_upload_mode_in_effect(h) in (GATED, SEQUENTIAL)
         L.vit_destroy(h)
+
+
+def test_argument_checks_of_the_host_code(sim, O):
+    """the C ABI's argument validation (csrc/vit_api.cu launch / vit_run / vit_create / vit_stream_push), which returns codes
+    and messages instead of faulting in a kernel"""
+    L = sim
+    L.vit_run_device_batch.restype = C.c_int
+    L.vit_run_device_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]
+    L.sim_device_alloc.restype, L.sim_device_alloc.argtypes = C.c_void_p, [C.c_size_t]
+    L.sim_device_free.restype, L.sim_device_free.argtypes = None, [C.c_void_p]
+    h = C.c_void_p()
+    assert L.vit_create(C.byref(h), 0x013, 0, 0) == 1 and b"unsupported" in L.vit_last_error()        # b16 x s16
+    assert L.vit_create(C.byref(h), 0x2021, 0, 0) == 1                                                   # no half2 DPX code
+    assert L.vit_create(None, 0x011, 0, 0) == 3
+    h = _make(L, 0x111)
+    N = 2 * ((W * 4) * 16 + 64)
+    d_in, d_out = L.sim_device_alloc(N // 2 + 64), L.sim_device_alloc(4096)
+    assert L.vit_run_device_batch(h, d_in + 4, d_out, N, 1, 0, 0, None, None) == 3 and b"16-byte aligned" in L.vit_last_error()
+    assert L.vit_run_device_batch(h, d_in, d_out, N, 2, 100, 512, None, None) == 3 and b"16-byte aligned" in L.vit_last_error()
+    assert L.vit_run_device_batch(h, d_in, d_out + 1, N, 1, 0, 0, None, None) == 3 and b"2-byte packs" in L.vit_last_error()
+    assert L.vit_run_device_batch(h, d_in, d_out, N, 70000, 0, 0, None, None) == 3 and b"65535" in L.vit_last_error()
+    assert L.vit_run_device_batch(h, None, d_out, N, 1, 0, 0, None, None) == 3
+    assert L.vit_run_device_batch(h, d_in, d_out, 100, 1, 0, 0, None, None) == 0                          # shorter than the window: nothing to decode
+    assert L.vit_run(h, None, None, N, None) == 3
+    assert L.vit_set_upload_mode(h, 7) == 3 and b"unknown upload mode" in L.vit_last_error()
+    out = np.zeros(8, np.uint8)
+    nout = C.c_size_t(99)
+    words = np.zeros(3, np.uint32)
+    assert L.vit_stream_push(h, words.ctypes.data, 7, out.ctypes.data, 8, C.byref(nout)) == 3 and b"whole 32-bit channel packs" in L.vit_last_error()
+    big = np.zeros(4000, np.uint32)
+    assert L.vit_stream_push(h, big.ctypes.data, 4000 * 8, out.ctypes.data, 8, C.byref(nout)) == 3 and b"output buffer holds" in L.vit_last_error()
+    assert nout.value == 0
+    L.sim_device_free(d_in)
+    L.sim_device_free(d_out)
+    L.vit_destroy(h)
+    L.vit_destroy(None)
