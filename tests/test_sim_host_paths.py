@@ -10,6 +10,7 @@ geometry, strided copies, gates, staging, downloads, carry arithmetic -- and com
 stream shapes than the GPU suite samples.  The product has no CPU path: this library exists only in the tests."""
 import ctypes as C
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -260,3 +261,46 @@ def test_argument_checks_of_the_host_code(sim, O):
     L.sim_device_free(d_out)
     L.vit_destroy(h)
     L.vit_destroy(None)
+
+
+_LOST_GATE = r'''
+import ctypes as C, sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+from oracle import oracle as O
+L = C.CDLL(%(so)r)
+vp, sz = C.c_void_p, C.c_size_t
+L.vit_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, sz]
+L.vit_run.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_float)]
+L.vit_set_segments.argtypes = [vp, C.c_uint]; L.vit_set_upload_mode.argtypes = [vp, C.c_int]
+L.vit_upload_mode_in_effect.argtypes = [vp]; L.vit_launch_count.argtypes = [vp]; L.vit_launch_count.restype = C.c_ulonglong
+L.vit_last_error.restype = C.c_char_p; L.vit_destroy.argtypes = [vp]
+L.sim_violations.restype = C.c_ulonglong
+opt, W = 0x004, 64
+n_bits = (W * 130 + 5) * 32 + 64          # fp32: 2.1 MB of input, 44 super-steps -> the automatic mode takes the time-sliced upload
+bits, packed, N = O.make_channel_det(n_bits, 4, seed=3, sigma=0.8)
+O.set_segments(W); exp = O.decode(opt, packed, N); O.set_segments(0)
+raw = np.ascontiguousarray(packed).view(np.uint8)[:O.input_size(opt, N)].copy()
+h = vp(); assert L.vit_create(C.byref(h), opt, 0, 0) == 0; L.vit_set_segments(h, W)
+assert L.vit_upload_mode_in_effect(h) == 3                      # AUTO resolves to the time-sliced upload
+out = np.zeros(O.output_size(opt, N), np.uint8)
+assert L.vit_run(h, raw.ctypes.data, out.ctypes.data, N, None) == 0, L.vit_last_error()
+assert np.array_equal(out.view(exp.dtype), exp)                # the last gate never opened: decoded again through the fallback
+assert L.vit_launch_count(h) == 2 and L.vit_upload_mode_in_effect(h) == 2       # ... and the handle stops using gates
+out[:] = 0
+assert L.vit_run(h, raw.ctypes.data, out.ctypes.data, N, None) == 0 and np.array_equal(out.view(exp.dtype), exp)
+assert L.vit_launch_count(h) == 3
+L.vit_set_upload_mode(h, 3)                                      # insisting on the time-sliced upload reports the time-out instead
+assert L.vit_run(h, raw.ctypes.data, out.ctypes.data, N, None) == 2 and b"upload gate timed out" in L.vit_last_error()
+L.vit_destroy(h)
+assert L.sim_violations() == 0
+print("OK")
+'''
+
+
+def test_lost_gate_falls_back_and_disables_gates(sim_lib_path):
+    """VIT_TEST_LOSE_GATE (the last gate's flag copy is skipped): the kernel's warps give up at the closed gate, vit_run sees
+    it, decodes again without gates and stops using them on that handle; with the time-sliced mode forced it is an error."""
+    import sys
+    code = _LOST_GATE % dict(root=ROOT, tests=os.path.join(ROOT, "tests"), so=sim_lib_path)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VIT_TEST_LOSE_GATE="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-1500:] + r.stderr[-2500:]
