@@ -64,3 +64,21 @@ def test_harness_at_a_noisy_point_counts_errors(fake):
     assert r.returncode == 0
     ben = int(re.search(r"BEN: (\d+)", r.stdout).group(1))
     assert 0 < ben < 200000 // 10
+
+
+@pytest.mark.parametrize("args", [
+    ["-n", "1000000", "-s", "5.5", "-m", "b32", "-i", "h", "--seed", "1"],            # BASELINE.json configs[0], as ./main runs it
+    ["-n", "250000", "-i", "s8", "-m", "f16", "-o", "b16", "-s", "3", "--seed", "3", "--prbs"],
+])
+def test_harness_over_the_real_host_code_and_kernel_source(sim_lib_path, args):
+    """The same harness over the library's OWN host code and kernel source: tests/sim/libvitsim.so (csrc/vit_api.cu compiled
+    for the host + stand-in CUDA runtime + the kernel source in the emulator) preloaded in front of libvitb200.so.  Everything
+    but the CUDA runtime and the GPU is the product: flags, pipeline, C++ shim, C ABI, vit_run, the 6400-segment kernel."""
+    exe = os.path.join(HOST, "main")
+    env = dict(os.environ, LD_PRELOAD=sim_lib_path, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-800:]
+    assert int(re.search(r"BEN: (\d+)", r.stdout).group(1)) == 0, r.stdout[-400:]
+    n = int(args[1])
+    bpp = 16 if "-o" in args and args[args.index("-o") + 1] == "b16" else 32
+    assert int(re.search(r"decoded: (\d+) bits", r.stdout).group(1)) == (n - 64) // bpp * bpp
