@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# VIT_B200_LIB: another build of the same library (e.g. one compiled for other generator polynomials, csrc/vit_code.h)
+# VIT_B200_LIB: another build of the same library (e.g. one compiled for other generator polynomials, csrc/vit_code.h).  An
+# explicit choice made before import, never a fallback: if the named file is missing, lib() raises like for the default.
 LIB_PATH = os.environ.get("VIT_B200_LIB") or os.path.join(_HERE, "libvitb200.so")
 
 # option bitfield, reference src/viterbi/viterbi.h:7-20
