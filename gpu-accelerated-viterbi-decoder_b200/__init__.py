@@ -29,6 +29,7 @@ constLen, polyn1, polyn2 = 7, 0o171, 0o133
 extraL, extraR, slideSize, forwardLen = 26, 38, 32, 96
 SEGMENTS = 6400
 UPLOAD_AUTO, UPLOAD_SEQUENTIAL, UPLOAD_CHUNKED, UPLOAD_GATED = 0, 1, 2, 3
+GEOMETRY_L8, GEOMETRY_L1 = 0, 1          # vit_set_geometry: lane geometry of gate-free launches (L1: experimental, many streams)
 
 
 class ViterbiError(RuntimeError):
@@ -94,6 +95,8 @@ def lib():
         L.vit_synth_device.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, vp, vp, vp]
         L.vit_set_upload_mode.restype, L.vit_set_upload_mode.argtypes = C.c_int, [vp, C.c_int]
         L.vit_upload_mode_in_effect.restype, L.vit_upload_mode_in_effect.argtypes = C.c_int, [vp]
+        L.vit_set_geometry.restype, L.vit_set_geometry.argtypes = C.c_int, [vp, C.c_int]
+        L.vit_last_launch_geometry.restype, L.vit_last_launch_geometry.argtypes = C.c_int, [vp]
         L.vit_synth_device_ex.restype = C.c_int
         L.vit_synth_device_ex.argtypes = [C.c_int, sz, C.c_uint, C.c_int, C.c_double, C.c_int, C.c_int, vp, vp, vp]
         L.vit_count_errors_synth_device.restype = C.c_int
@@ -277,6 +280,13 @@ class ViterbiCUDA:
     def set_upload_mode(self, mode):
         """UPLOAD_AUTO / _SEQUENTIAL / _CHUNKED / _GATED: how run() moves host buffers (vit_set_upload_mode)."""
         _check(lib().vit_set_upload_mode(self._h, int(mode)))
+
+    def set_geometry(self, geometry):
+        """GEOMETRY_L8 (default) / GEOMETRY_L1 (experimental: one lane per segment, for launches of a dozen streams and more)"""
+        _check(lib().vit_set_geometry(self._h, int(geometry)))
+
+    def last_launch_geometry(self):
+        return int(lib().vit_last_launch_geometry(self._h))
 
     def upload_mode_in_effect(self):
         return int(lib().vit_upload_mode_in_effect(self._h))

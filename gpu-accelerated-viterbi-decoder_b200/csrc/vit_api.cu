@@ -166,6 +166,12 @@ struct vit_handle {
     unsigned last_stage_out = 0;                                     // KParams::stage_out of the last launch
     bool force_stage_out = getenv("VIT_STAGE_OUT") != nullptr;       // measurement hook: staged output stores for local buffers too
     int upload_mode = VIT_UPLOAD_AUTO;    // vit_set_upload_mode
+    int geometry = env_geometry();        // vit_set_geometry: lane geometry of gate-free launches
+    int last_geometry = VIT_GEOMETRY_L8;
+    static int env_geometry() {
+        const char* e = getenv("VIT_GEOMETRY");
+        return e && (strcmp(e, "l1") == 0 || strcmp(e, "L1") == 0 || strcmp(e, "1") == 0) ? VIT_GEOMETRY_L1 : VIT_GEOMETRY_L8;
+    }
     unsigned long long gate_timeout_ns = 2000000000ull;
     StagePool* pool = nullptr;            // created on the first vit_run with pageable buffers
     static bool env_forbids_gates() {
@@ -233,8 +239,11 @@ int launch_range(vit_handle* h, const void* in_d, void* out_d, size_t inputNum, 
         kp.gate_n = gp->n;
         for (unsigned i = 0; i < gp->n; i++) kp.gate_super[i] = gp->super[i];
     }
+    // the experimental one-lane-per-segment geometry: only where the launch needs neither upload gates nor staged stores
+    const bool l1 = h->geometry == VIT_GEOMETRY_L1 && h->kernel->launch_l1 && kp.gate_n == 0 && kp.stage_out == 0;
+    h->last_geometry = l1 ? VIT_GEOMETRY_L1 : VIT_GEOMETRY_L8;
     if (e0) VIT_CUDA(cudaEventRecord(e0, st));
-    VIT_CUDA(h->kernel->launch(kp, st));
+    VIT_CUDA(l1 ? h->kernel->launch_l1(kp, st) : h->kernel->launch(kp, st));
     h->launches++;
     if (e1) VIT_CUDA(cudaEventRecord(e1, st));
     return VIT_OK;
@@ -758,6 +767,15 @@ int vit_set_upload_mode(vit_handle* h, int mode) {
     h->upload_mode = mode;
     return VIT_OK;
 }
+
+int vit_set_geometry(vit_handle* h, int geometry) {
+    if (!h) return fail(VIT_ERR_ARG, "null handle");
+    if (geometry != VIT_GEOMETRY_L8 && geometry != VIT_GEOMETRY_L1) return fail(VIT_ERR_ARG, "unknown geometry %d", geometry);
+    h->geometry = geometry;
+    return VIT_OK;
+}
+
+int vit_last_launch_geometry(const vit_handle* h) { return h ? h->last_geometry : VIT_GEOMETRY_L8; }
 
 int vit_upload_mode_in_effect(const vit_handle* h) {
     if (!h) return -1;

@@ -2,4 +2,5 @@
 #define VIT_INST_MET MET_B16
 #define VIT_INST_FN kernel_entry_b16
 #define VIT_INST_HAS_S16 0
+#define VIT_INST_HAS_L1 1
 #include "vit_inst.inc"

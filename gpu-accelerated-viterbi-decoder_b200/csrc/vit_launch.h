@@ -9,6 +9,9 @@ struct KernelEntry {
     cudaError_t (*launch)(const KParams& kp, cudaStream_t stream);
     const void* func;
     int smem_bytes;
+    // the same launch with the one-lane-per-segment geometry (vit_kernel_l1.inc), or nullptr where it is not built; ignores
+    // upload gates and staged output stores (the caller only uses it where neither is needed)
+    cudaError_t (*launch_l1)(const KParams& kp, cudaStream_t stream);
 };
 // met: MET_*, in: IN_*, bpp16: 0/1.  Returns nullptr for combinations that are not built.
 const KernelEntry* kernel_entry(int met, int in, int bpp16);

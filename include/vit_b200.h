@@ -131,6 +131,20 @@ int vit_options_valid_ref(int options);
  * threads per block, stream segments per block.  Returns non-zero if the kernel is missing. */
 int vit_kernel_info(int options, int* regs, int* smem_bytes, int* block_threads, int* segs_per_block);
 
+/* Lane geometry of the decode kernel for this handle's gate-free launches (vit_run_device, vit_run_device_batch, the stream
+ * job; vit_run's time-sliced upload always uses L8).
+ *   L8 (default)  8 lanes per segment, 4 segments per warp: the measured product kernel.
+ *   L1            one lane per segment, 32 segments per warp (csrc/vit_kernel_l1.inc): no lane exchanges, no operand table.
+ *                 EXPERIMENTAL: bit-exact against the golden model in the emulator and against L8 on a B200, measured once
+ *                 (119.2 against 108.8 Gb/s on 16 streams per launch, profiles/r2_l1_bench.txt).  A stream is only 200 such
+ *                 warps, so it pays from about a dozen streams per launch; packed cores (b16, f16) and local output buffers
+ *                 only -- a launch that does not qualify uses L8.
+ * The environment variable VIT_GEOMETRY=l1 sets the initial value of every handle.  Results are identical. */
+enum { VIT_GEOMETRY_L8 = 0, VIT_GEOMETRY_L1 = 1 };
+int vit_set_geometry(vit_handle* h, int geometry);
+/* the geometry the last launch actually ran with */
+int vit_last_launch_geometry(const vit_handle* h);
+
 /* launches issued by this handle so far (one decode kernel per run) */
 unsigned long long vit_launch_count(const vit_handle* h);
 

@@ -14,6 +14,10 @@ for S in 8 12 16 24 48; do
 done
 $NV -DL1_STREAMS=16 -o /tmp/l1_bench scripts/l1_bench.cu
 ncu --set full --clock-control none --import-source on -k regex:vit_decode_kernel_l1 -c 1 -o $OUT/l1_s8_16streams /tmp/l1_bench > $OUT/ncu_l1.log 2>&1
+VIT_TEST_L1=1 python -m pytest tests/test_gpu_l1_geometry.py -q -m gpu > $OUT/pytest_l1.txt 2>&1    # L1 through the library
+for W in 16 32; do
+  VIT_GEOMETRY=l1 python bench.py --workload config5 --streams 128 --wave $W --batch 64 --gather none > $OUT/c5_128streams_l1_wave$W.json 2> $OUT/c5_l1_wave$W.err
+done
 for W in 8 16 32; do
   python bench.py --workload config5 --streams 128 --wave $W --batch 64 > $OUT/c5_128streams_wave$W.json 2> $OUT/c5_wave$W.err
 done

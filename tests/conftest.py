@@ -53,7 +53,7 @@ def _sim_target():
     srcs = [api, os.path.join(SIM_DIR, "sim_runtime.cpp"), os.path.join(EMU_DIR, "vit_emu.cpp"), os.path.join(SIM_DIR, "sim_stubs.cpp"),
             os.path.join(SIM_DIR, "cuda_runtime.h"), os.path.join(ROOT, "include", "vit_b200.h")] + KERNEL_SRCS
     srcs += [os.path.join(PKG_DIR, "csrc", f) for f in ("vit_stage_pool.h", "vit_launch.h", "vit_internal.h")]
-    return so, srcs, [GXX, "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIT_EMU_L8_ONLY", "-I", SIM_DIR, "-x", "c++",
+    return so, srcs, [GXX, "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIT_EMU_L8_ONLY", "-DVIT_EMU_WITH_L1", "-I", SIM_DIR, "-x", "c++",
                       api, srcs[1], srcs[2], srcs[3], "-o", so]
 
 

@@ -102,10 +102,13 @@ Job g_job;
 
 template <int MET, int IN, int BPP>
 void run_lane(int lane) {
-#if !defined(VIT_EMU_L8_ONLY)   // (builds for other code parameters instantiate the product geometry only: a third of the compile time)
+#if !defined(VIT_EMU_L8_ONLY) || defined(VIT_EMU_WITH_L1)
     if (g_job.lanes == 1) {
         vitk::l1::warp_body_l1<MET, IN, BPP>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
-    } else if (g_job.lanes == 16) {
+    } else
+#endif
+#if !defined(VIT_EMU_L8_ONLY)   // (builds for other code parameters instantiate the product geometry only: a third of the compile time)
+    if (g_job.lanes == 16) {
         if (g_job.tbl == 32) vitk::l16::warp_body<MET, IN, BPP, 32>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
         else vitk::l16::warp_body<MET, IN, BPP, 96>(g_job.kp, g_job.warp, g_job.stream, lane, g_job.smem);
     } else if (g_job.lanes == 4) {
@@ -168,7 +171,9 @@ static unsigned g_seg_first = 0, g_seg_limit = 0;   // 0, 0: the whole stream
 extern "C" void vit_emu_set_segment_range(unsigned first, unsigned limit) { g_seg_first = first; g_seg_limit = limit; }
 extern "C" void vit_emu_set_stage_out(int on) { g_stage_out = on ? 1u : 0u; }
 extern "C" void vit_emu_set_table(int tbl) { g_job.tbl = tbl == 32 ? 32 : 96; }
-#if defined(VIT_EMU_L8_ONLY)
+#if defined(VIT_EMU_L8_ONLY) && defined(VIT_EMU_WITH_L1)
+extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 1 ? 1 : 8; }
+#elif defined(VIT_EMU_L8_ONLY)
 extern "C" void vit_emu_set_lanes(int) { g_job.lanes = 8; }
 #else
 extern "C" void vit_emu_set_lanes(int lanes) { g_job.lanes = lanes == 4 ? 4 : lanes == 16 ? 16 : lanes == 1 ? 1 : 8; }
@@ -211,10 +216,10 @@ static void run_grid() {
 
 // a launch exactly as the library's host code describes it (tests/sim: csrc/vit_api.cu compiled for the host hands its
 // KParams to the emulator instead of a GPU); product lane geometry, operand-table build `tbl`
-void vit_emu_run_kparams(const vitk::KParams& kp, int met, int in, int bpp, int tbl) {
+void vit_emu_run_kparams(const vitk::KParams& kp, int met, int in, int bpp, int tbl, int lanes) {
     g_job.kp = kp;
     g_job.met = met; g_job.in = in; g_job.bpp = bpp;
-    g_job.lanes = 8; g_job.tbl = tbl == 32 ? 32 : 96;
-    g_in_base = kp.in; g_cur_lanes = 8;
+    g_job.lanes = lanes == 1 ? 1 : 8; g_job.tbl = tbl == 32 ? 32 : 96;
+    g_in_base = kp.in; g_cur_lanes = (unsigned)g_job.lanes;
     run_grid();
 }

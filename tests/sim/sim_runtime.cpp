@@ -23,7 +23,7 @@
 
 #include "../../gpu-accelerated-viterbi-decoder_b200/csrc/vit_launch.h"
 
-void vit_emu_run_kparams(const vitk::KParams& kp, int met, int in, int bpp, int tbl);   // tests/emu/vit_emu.cpp
+void vit_emu_run_kparams(const vitk::KParams& kp, int met, int in, int bpp, int tbl, int lanes);   // tests/emu/vit_emu.cpp
 
 namespace {
 
@@ -31,7 +31,7 @@ struct Op {
     enum Kind { COPY, COPY2D, LAUNCH, RECORD, WAIT } kind;
     void* dst = nullptr; const void* src = nullptr; size_t n = 0, dpitch = 0, spitch = 0, width = 0, height = 0;
     SimEvent* ev = nullptr; unsigned long long ticket = 0;
-    vitk::KParams kp{}; int met = 0, in = 0, bpp = 0;
+    vitk::KParams kp{}; int met = 0, in = 0, bpp = 0, lanes = 8;
     std::vector<std::vector<uint8_t>> attempts;      // output snapshots of the gate-limited attempts
 };
 }  // namespace
@@ -61,7 +61,7 @@ bool in_range(const std::map<const char*, size_t>& m, const void* p) {
 bool run_launch(Op& op, bool final_attempt) {
     const bool gated = op.kp.gate_n > 0;
     if (!gated) {
-        vit_emu_run_kparams(op.kp, op.met, op.in, op.bpp, g_tbl);
+        vit_emu_run_kparams(op.kp, op.met, op.in, op.bpp, g_tbl, op.lanes);
         g_kernel_runs++;
         return true;
     }
@@ -71,7 +71,7 @@ bool run_launch(Op& op, bool final_attempt) {
     memset(op.kp.out, 0xDE, nb);
     const unsigned err_before = *op.kp.gate_err;
     *op.kp.gate_err = 0;
-    vit_emu_run_kparams(op.kp, op.met, op.in, op.bpp, g_tbl);
+    vit_emu_run_kparams(op.kp, op.met, op.in, op.bpp, g_tbl, op.lanes);
     g_kernel_runs++; g_gated_attempts++;
     const bool gave_up = *op.kp.gate_err != 0;
     if (gave_up && !final_attempt) {
@@ -239,8 +239,8 @@ cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t 
 // ---- kernel table: every (core, input type, pack width) "kernel" is the emulator --------------------------------------
 namespace vitk {
 namespace {
-cudaError_t enqueue_launch(const KParams& kp, cudaStream_t st, int met, int in, int bpp) {
-    Op op; op.kind = Op::LAUNCH; op.kp = kp; op.met = met; op.in = in; op.bpp = bpp;
+cudaError_t enqueue_launch(const KParams& kp, cudaStream_t st, int met, int in, int bpp, int lanes = 8) {
+    Op op; op.kind = Op::LAUNCH; op.kp = kp; op.met = met; op.in = in; op.bpp = bpp; op.lanes = lanes;
     // a gate-waiting kernel is launched BEFORE its input is uploaded: whatever an earlier call left in the device buffer
     // must not be able to stand in for bytes that have not arrived yet
     if (kp.gate_n > 0) memset(const_cast<uint8_t*>(kp.in), 0xCD, (size_t)kp.in_bytes);
@@ -248,8 +248,10 @@ cudaError_t enqueue_launch(const KParams& kp, cudaStream_t st, int met, int in, 
     return cudaSuccess;
 }
 template <int MET, int IN, int BPP> cudaError_t sim_launch(const KParams& kp, cudaStream_t st) { return enqueue_launch(kp, st, MET, IN, BPP); }
+template <int MET, int IN, int BPP> cudaError_t sim_launch_l1(const KParams& kp, cudaStream_t st) { return enqueue_launch(kp, st, MET, IN, BPP, 1); }
 template <int MET> const KernelEntry* entry(int in, int bpp16) {
-#define E(IN, BPP) {&sim_launch<MET, IN, BPP>, (const void*)&sim_launch<MET, IN, BPP>, 0}
+    // as in the library: the one-lane-per-segment geometry exists for the packed cores only
+#define E(IN, BPP) {&sim_launch<MET, IN, BPP>, (const void*)&sim_launch<MET, IN, BPP>, 0, (MET == MET_B16 || MET == MET_F16) ? &sim_launch_l1<MET, IN, BPP> : nullptr}
     static const KernelEntry table[5][2] = {{E(0, 32), E(0, 16)}, {E(1, 32), E(1, 16)}, {E(2, 32), E(2, 16)}, {E(3, 32), E(3, 16)}, {E(4, 32), E(4, 16)}};
 #undef E
     if (in < 0 || in > 4) return nullptr;

@@ -131,3 +131,50 @@ def test_entry_points_that_need_a_gpu_say_so(VS):
         VS.synth_device(1, 1000, 0)
     assert VS.options_valid(0x122) and not VS.options_valid(0x013) and VS.options_valid_ref(0x011) and not VS.options_valid_ref(0x122)
     assert VS.parse_options("s8", "f16", "b16") == 0x122
+
+
+@pytest.mark.parametrize("opt", [0x012, 0x111, 0x024])
+def test_one_lane_geometry_through_the_library(VS, O, opt):
+    """vit_set_geometry(L1) (experimental, opt-in): gate-free launches of the packed cores run the one-lane-per-segment kernel
+    -- same words -- while vit_run's time-sliced upload keeps the 8-lane kernel (it needs the upload gates), and so does a
+    core the geometry is not built for."""
+    import ctypes as C
+    L = VS.lib()
+    ns = 3
+    bpp = 16 if opt & 0x100 else 32
+    streams = [O.make_channel_det((W * 9 + 5) * bpp + 64 + 3, opt & 0xF, seed=80 + s, sigma=0.8) for s in range(ns)]
+    N = streams[0][2]
+    dec = VS.ViterbiCUDA(opt)
+    dec.set_segments(W)
+    assert dec.last_launch_geometry() == VS.GEOMETRY_L8
+    dec.set_geometry(VS.GEOMETRY_L1)
+    in_bytes, out_bytes = dec.getInputSize(N), dec.getOutputSize(N)
+    in_stride, out_stride = (in_bytes + 255) // 256 * 256, (out_bytes + 255) // 256 * 256
+    d_in, d_out = C.c_void_p(), C.c_void_p()
+    assert L.vit_dev_alloc(C.byref(d_in), ns * in_stride) == 0 and L.vit_dev_alloc(C.byref(d_out), ns * out_stride) == 0
+    for s, (_, packed, _) in enumerate(streams):
+        raw = np.ascontiguousarray(packed).view(np.uint8)[:in_bytes].copy()
+        assert L.vit_dev_copy_from_host(d_in.value + s * in_stride, raw.ctypes.data, in_bytes) == 0
+    dec.run_device(d_in.value, d_out.value, N, nstreams=ns, in_stride=in_stride, out_stride=out_stride)
+    assert L.vit_dev_sync() == 0 and dec.last_launch_geometry() == VS.GEOMETRY_L1
+    for s, (_, packed, _) in enumerate(streams):
+        got = VS.dev_to_host(d_out.value + s * out_stride, out_bytes).view(dec.decPack_t)
+        assert np.array_equal(got, _oracle(O, opt, packed, N)), s
+    # host buffers, plain sequence: L1 as well; time-sliced upload: the 8-lane kernel
+    big = O.make_channel_det((W * 24) * 32 + 64, opt & 0xF, seed=90, sigma=0.8)        # >= 8 super-steps per segment
+    out = dec.run(big[1], big[2], want_kernel_time=True)[0]
+    assert np.array_equal(out, _oracle(O, opt, big[1], big[2])) and dec.last_launch_geometry() == VS.GEOMETRY_L1
+    dec.set_upload_mode(VS.UPLOAD_GATED)
+    assert np.array_equal(dec.run(big[1], big[2]), out) and dec.last_launch_geometry() == VS.GEOMETRY_L8
+    with pytest.raises(VS.ViterbiError):
+        dec.set_geometry(5)
+    L.vit_dev_free(d_in)
+    L.vit_dev_free(d_out)
+    dec.close()
+    d32 = VS.ViterbiCUDA(0x001)                                       # int32 core: the geometry is not built for it
+    d32.set_segments(W)
+    d32.set_geometry(VS.GEOMETRY_L1)
+    small = O.make_channel_det((W * 3) * 32 + 64, 1, seed=91, sigma=0.8)
+    assert np.array_equal(d32.run(small[1], small[2], want_kernel_time=True)[0], _oracle(O, 0x001, small[1], small[2]))
+    assert d32.last_launch_geometry() == VS.GEOMETRY_L8
+    d32.close()
